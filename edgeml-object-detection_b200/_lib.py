@@ -1,0 +1,88 @@
+"""ctypes binding of liborie_b200.so (C ABI declared in include/orie_b200.h).
+
+There is no CPU fallback: if the shared library is missing and cannot be built
+with nvcc, importing the engine fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_i64p = C.c_void_p   # device pointers are passed as plain addresses
+SYMBOLS = [
+    "orie_last_error", "orie_version", "orie_match", "orie_dcsb",
+    "orie_index_build", "orie_index_destroy", "orie_index_info",
+    "orie_ensemble_from_indices", "orie_ensemble_sample",
+    "orie_reward_workspace_bytes", "orie_reward",
+]
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [
+        ("num_images", C.c_int64), ("num_classes", C.c_int64),
+        ("num_thresholds", C.c_int32), ("seg_chunks", C.c_int32),
+        ("num_weak", C.c_int64), ("num_strong", C.c_int64), ("num_labels", C.c_int64),
+        ("slots", C.c_int64), ("segments", C.c_int64), ("events", C.c_int64),
+        ("label_slots", C.c_int64), ("label_segments", C.c_int64),
+        ("class_groups", C.c_int64), ("ens_words", C.c_int64), ("device_bytes", C.c_int64),
+    ]
+
+
+class OrieError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"orie_b200 error {code}: {message}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the sources are newer) and type the library."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path) or (_build.stale() and os.path.exists(_build.nvcc_or_none() or "")):
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    "liborie_b200.so is missing and could not be built; the engine has no CPU fallback. "
+                    f"Build it with `python -c 'import __graft_entry__ as g; g.build()'` ({e})") from e
+    lib = C.CDLL(path)
+    vp, i64, i32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_uint64
+    lib.orie_last_error.restype = C.c_char_p
+    lib.orie_last_error.argtypes = []
+    lib.orie_version.restype = C.c_int
+    lib.orie_match.restype = C.c_int
+    lib.orie_match.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(C.c_double), i32, i64, vp, vp, vp, vp]
+    lib.orie_dcsb.restype = C.c_int
+    lib.orie_dcsb.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    lib.orie_index_build.restype = C.c_int
+    lib.orie_index_build.argtypes = [i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, C.POINTER(vp)]
+    lib.orie_index_destroy.restype = None
+    lib.orie_index_destroy.argtypes = [vp]
+    lib.orie_index_info.restype = C.c_int
+    lib.orie_index_info.argtypes = [vp, C.POINTER(IndexInfo)]
+    lib.orie_ensemble_from_indices.restype = C.c_int
+    lib.orie_ensemble_from_indices.argtypes = [vp, i64, i64, vp, i64, vp, vp, vp]
+    lib.orie_ensemble_sample.restype = C.c_int
+    lib.orie_ensemble_sample.argtypes = [vp, i64, i64, i64, u64, vp, vp]
+    lib.orie_reward_workspace_bytes.restype = C.c_size_t
+    lib.orie_reward_workspace_bytes.argtypes = [vp, i64]
+    lib.orie_reward.restype = C.c_int
+    lib.orie_reward.argtypes = [vp, i64, i64, vp, i64, vp, C.c_size_t, vp, vp, vp]
+    _LIB = lib
+    return lib
+
+
+def check(code: int):
+    if code != 0:
+        raise OrieError(code, load().orie_last_error().decode("utf-8", "replace"))

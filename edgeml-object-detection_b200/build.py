@@ -1,0 +1,55 @@
+"""Build liborie_b200.so in-tree with nvcc for sm_100a (no other target)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "liborie_b200.so")
+SOURCES = ["api.cu", "sort.cu", "match.cu", "index.cu", "reward.cu"]
+HEADERS = ["common.cuh", "index.cuh", os.path.join("..", "..", "include", "orie_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",                    # FP64 parity: never contract a*b+c
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared", "-cudart", "static",
+]
+
+
+def nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; the engine has no CPU fallback and cannot be built without it")
+    return exe
+
+
+def nvcc_or_none():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    return exe if os.path.exists(exe) else None
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return LIB
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

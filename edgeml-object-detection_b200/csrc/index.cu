@@ -1,0 +1,581 @@
+// Dataset index build (orie_index_build): everything about the ORIE computation
+// that does not depend on the target or on its ensemble is computed here once.
+//
+// reward.py:40-49 gathers N+1 cached records and lib/metrics.py:100-104 re-sorts
+// them by confidence for EVERY target.  The relative order of two detections never
+// changes between targets, so the engine sorts the weak detections of the whole
+// dataset once by (class asc, confidence desc, image, row) with the radix sort in
+// sort.cu and lays them out in "slots"; an ensemble then only selects a subset of
+// slots (reward.cu).  See DESIGN.md §3 for the layout.
+#include <algorithm>
+#include <vector>
+
+#include "index.cuh"
+
+namespace orie {
+
+// ----------------------------------------------------------------------------
+// small kernels
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t conf_desc_key(double c) {
+    // order-isomorphic to "descending double": smaller key <=> larger confidence
+    uint64_t b = (uint64_t)__double_as_longlong(c);
+    uint64_t asc = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+    return ~asc;
+}
+
+__global__ void image_of_row_kernel(const int64_t *__restrict__ off, int64_t M, int64_t n, uint32_t *__restrict__ img,
+                                    int32_t *__restrict__ status) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int64_t lo = 0, hi = M;  // largest i with off[i] <= k
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (off[mid] <= k) lo = mid; else hi = mid;
+    }
+    img[k] = (uint32_t)lo;
+    if (off[lo + 1] - off[lo] > 65535) atomicOr(status, 1);
+}
+
+__global__ void conf_keys_kernel(const double *__restrict__ conf, int64_t n, uint64_t *__restrict__ keys,
+                                 uint32_t *__restrict__ vals) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    keys[k] = conf_desc_key(conf[k]);
+    vals[k] = (uint32_t)k;
+}
+
+// keys[k] = (src[vals[k]] >> shift)
+__global__ void gather_keys_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ vals, int64_t n,
+                                   int shift, uint64_t *__restrict__ keys) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    keys[k] = (uint64_t)(src[vals[k]] >> shift);
+}
+
+__global__ void class_hist_kernel(const int32_t *__restrict__ cls, int64_t n, int64_t C, uint32_t *__restrict__ hist,
+                                  int32_t *__restrict__ status) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int c = cls[k];
+    if (c < 0 || c >= C) { atomicOr(status, 2); return; }
+    atomicAdd(&hist[c], 1u);
+}
+
+__global__ void fill_u32_kernel(uint32_t *__restrict__ p, int64_t n, uint32_t v) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) p[k] = v;
+}
+
+// rank r of the sorted weak order -> slot
+__global__ void place_slots_kernel(const uint32_t *__restrict__ order, const int32_t *__restrict__ cls,
+                                   const uint32_t *__restrict__ img, const uint16_t *__restrict__ tp,
+                                   const double *__restrict__ conf, int64_t n, const uint32_t *__restrict__ cls_off,
+                                   const uint32_t *__restrict__ pad_off, uint32_t *__restrict__ slot_img,
+                                   uint16_t *__restrict__ slot_tp, uint32_t *__restrict__ prank,
+                                   double *__restrict__ conf_sorted) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t det = order[r];
+    const int c = cls[det];
+    const uint32_t slot = pad_off[c] + ((uint32_t)r - cls_off[c]);
+    slot_img[slot] = img[det];
+    slot_tp[slot] = tp[det];
+    prank[det] = slot;
+    conf_sorted[r] = conf[det];
+}
+
+// one warp per chunk
+__global__ void event_bits_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks, uint32_t *__restrict__ evbits,
+                                  uint32_t *__restrict__ evcnt) {
+    int64_t ch = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ch >= nchunks) return;
+    const int lane = threadIdx.x & 31;
+    unsigned b = __ballot_sync(kFull, slot_tp[ch * 32 + lane] != 0);
+    if (lane == 0) { evbits[ch] = b; evcnt[ch] = __popc(b); }
+}
+
+__global__ void event_mask_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks,
+                                  const uint32_t *__restrict__ evbits, const uint32_t *__restrict__ evbase,
+                                  uint16_t *__restrict__ evmask) {
+    int64_t ch = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ch >= nchunks) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned b = evbits[ch];
+    if ((b >> lane) & 1u) evmask[evbase[ch] + __popc(b & ((1u << lane) - 1u))] = slot_tp[ch * 32 + lane];
+}
+
+__global__ void gather_seg_ev0_kernel(const int32_t *__restrict__ seg_chunk0, int64_t S, const uint32_t *__restrict__ evbase,
+                                      uint32_t *__restrict__ seg_ev0) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) seg_ev0[s] = evbase[seg_chunk0[s]];
+}
+
+// insertion slot of a strong detection in the weak stream: behind every weak detection of its
+// class whose confidence is >= its own (weak first on exact ties == stable concatenation order)
+__global__ void strong_query_kernel(const int32_t *__restrict__ cls, const double *__restrict__ conf, int64_t n,
+                                    const double *__restrict__ conf_sorted, const uint32_t *__restrict__ cls_off,
+                                    const uint32_t *__restrict__ pad_off, uint32_t *__restrict__ q) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int c = cls[k];
+    const double v = conf[k];
+    const double *seg = conf_sorted + cls_off[c];
+    int lo = 0, hi = (int)(cls_off[c + 1] - cls_off[c]);  // first index with seg[i] < v
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (seg[mid] >= v) lo = mid + 1; else hi = mid;
+    }
+    q[k] = pad_off[c] + (uint32_t)lo;
+}
+
+// own list entry i (image-major, sorted) <- detection vals[i]
+__global__ void own_fill_kernel(const uint32_t *__restrict__ vals, int64_t n, const uint32_t *__restrict__ q_of_det,
+                                const uint16_t *__restrict__ tp, uint32_t *__restrict__ own_q,
+                                uint16_t *__restrict__ own_m, uint32_t *__restrict__ ownpos_of_det) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t det = vals[i];
+    own_q[i] = q_of_det[det];
+    own_m[i] = tp[det];
+    ownpos_of_det[det] = (uint32_t)i;
+}
+
+// class start table of every image's own list: cs[img][c] = first local index with class >= c
+__global__ void own_class_start_kernel(const uint32_t *__restrict__ vals, int64_t n, const int32_t *__restrict__ cls,
+                                       const uint32_t *__restrict__ img, const int64_t *__restrict__ off, int64_t C,
+                                       uint16_t *__restrict__ cs) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t det = vals[i];
+    const uint32_t im = img[det];
+    const int c = cls[det];
+    const int64_t a = off[im], b = off[im + 1];
+    uint16_t *row = cs + (int64_t)im * (C + 1);
+    const int local = (int)(i - a);
+    if (i == a)
+        for (int cc = 0; cc <= c; ++cc) row[cc] = 0;
+    const int cnext = (i + 1 < b) ? cls[vals[i + 1]] : (int)C;
+    for (int cc = c + 1; cc <= cnext; ++cc) row[cc] = (uint16_t)(local + 1);
+}
+
+// batch-major query entry k <- detection vals[k]
+__global__ void batch_query_kernel(const uint32_t *__restrict__ vals, int64_t n, const uint32_t *__restrict__ q_of_det,
+                                   const uint32_t *__restrict__ img, const uint32_t *__restrict__ ownpos_of_det,
+                                   uint2 *__restrict__ bq) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t det = vals[k];
+    bq[k] = make_uint2(q_of_det[det], ((img[det] & 31u) << 27) | ownpos_of_det[det]);
+}
+
+// bqoff[b][s] = first entry of batch b with q >= first slot of segment s  (s == S: end of the batch)
+__global__ void batch_query_offsets_kernel(const uint2 *__restrict__ bq, const int64_t *__restrict__ off, int64_t M,
+                                           int64_t nbatch, const int32_t *__restrict__ seg_chunk0, int64_t S,
+                                           uint32_t *__restrict__ bqoff) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nbatch * (S + 1)) return;
+    const int64_t b = k / (S + 1), s = k % (S + 1);
+    const int64_t i0 = b * 32 < M ? b * 32 : M, i1 = (b + 1) * 32 < M ? (b + 1) * 32 : M;
+    int64_t lo = off[i0], hi = off[i1];
+    if (s < S) {
+        const uint32_t slot0 = (uint32_t)seg_chunk0[s] * 32u;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (bq[mid].x < slot0) lo = mid + 1; else hi = mid;
+        }
+    } else {
+        lo = hi;
+    }
+    bqoff[k] = (uint32_t)lo;
+}
+
+__global__ void place_labels_kernel(const uint64_t *__restrict__ keys_sorted, const uint32_t *__restrict__ img_sorted,
+                                    int64_t n, const uint32_t *__restrict__ cls_off, const uint32_t *__restrict__ pad_off,
+                                    uint32_t *__restrict__ slot_img) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int c = (int)keys_sorted[r];
+    slot_img[pad_off[c] + ((uint32_t)r - cls_off[c])] = img_sorted[r];
+}
+
+__global__ void label_keys_kernel(const int32_t *__restrict__ cls, const uint32_t *__restrict__ img, int64_t n, int64_t C,
+                                  uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ gtcnt) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int c = cls[k];
+    keys[k] = (uint64_t)(uint32_t)c;
+    vals[k] = img[k];
+    if (c >= 0 && c < C) atomicAdd(&gtcnt[(int64_t)img[k] * C + c], 1u);
+}
+
+static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
+    int b = 1;
+    while (((int64_t)1 << b) < n) ++b;
+    return b;
+}
+
+struct Builder {
+    orie_index *ix;
+    cudaStream_t st;
+    std::vector<void *> temps;
+    ~Builder() {
+        for (void *p : temps) cudaFree(p);
+    }
+    template <typename Tp>
+    int temp(Tp **p, int64_t count) {
+        void *q = nullptr;
+        ORIE_CUDA(cudaMalloc(&q, (size_t)std::max<int64_t>(count, 1) * sizeof(Tp)));
+        temps.push_back(q);
+        *p = (Tp *)q;
+        return ORIE_OK;
+    }
+    template <typename Tp>
+    int keep(Tp **p, int64_t count) {
+        void *q = nullptr;
+        size_t bytes = (size_t)std::max<int64_t>(count, 1) * sizeof(Tp);
+        ORIE_CUDA(cudaMalloc(&q, bytes));
+        if (ix->n_allocs >= (int)(sizeof(ix->allocs) / sizeof(ix->allocs[0]))) {
+            cudaFree(q);
+            set_error("orie_index_build: allocation table full");
+            return ORIE_EINVAL;
+        }
+        ix->allocs[ix->n_allocs++] = q;
+        ix->device_bytes += (int64_t)bytes;
+        *p = (Tp *)q;
+        return ORIE_OK;
+    }
+};
+
+static inline unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)std::max<int64_t>(ceil_div(n, threads), 1); }
+
+// Padded layout of one class-sorted stream on the host: per class padded length, then segments.
+struct StreamLayout {
+    std::vector<uint32_t> cls_off, pad_off;
+    std::vector<int32_t> seg_chunk0, seg_nch, cls_seg0;
+    int64_t P = 0;
+};
+
+static StreamLayout make_layout(const uint32_t *cnt, int64_t C, int extra_pad, int seg_chunks) {
+    StreamLayout L;
+    L.cls_off.resize(C + 1);
+    L.pad_off.resize(C + 1);
+    L.cls_seg0.resize(C + 1);
+    uint32_t a = 0, p = 0;
+    for (int64_t c = 0; c < C; ++c) {
+        L.cls_off[c] = a;
+        L.pad_off[c] = p;
+        L.cls_seg0[c] = (int32_t)L.seg_chunk0.size();
+        const int64_t padlen = round_up((int64_t)cnt[c] + extra_pad, kChunk);
+        const int nch = (int)(padlen / kChunk);
+        for (int k = 0; k < nch; k += seg_chunks) {
+            L.seg_chunk0.push_back((int32_t)(p / kChunk) + k);
+            L.seg_nch.push_back(std::min(seg_chunks, nch - k));
+        }
+        a += cnt[c];
+        p += (uint32_t)padlen;
+    }
+    L.cls_off[C] = a;
+    L.pad_off[C] = p;
+    L.cls_seg0[C] = (int32_t)L.seg_chunk0.size();
+    L.P = p;
+    return L;
+}
+
+template <typename Tp>
+static int upload(Builder &B, Tp **dst, const std::vector<Tp> &src, bool keep) {
+    if (keep) ORIE_TRY(B.keep(dst, (int64_t)src.size()));
+    else ORIE_TRY(B.temp(dst, (int64_t)src.size()));
+    if (!src.empty())
+        ORIE_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(Tp), cudaMemcpyHostToDevice, B.st));
+    return ORIE_OK;
+}
+
+static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
+                 const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
+                 const int64_t *l_off, const int32_t *l_cls, int seg_chunks_req, cudaStream_t st) {
+    Builder B{ix, st};
+    const int64_t M = ix->M, C = ix->C;
+    // ---- sizes (three small D2H reads)
+    int64_t tails[3];
+    ORIE_CUDA(cudaMemcpyAsync(&tails[0], w_off + M, 8, cudaMemcpyDeviceToHost, st));
+    ORIE_CUDA(cudaMemcpyAsync(&tails[1], s_off + M, 8, cudaMemcpyDeviceToHost, st));
+    ORIE_CUDA(cudaMemcpyAsync(&tails[2], l_off + M, 8, cudaMemcpyDeviceToHost, st));
+    ORIE_CUDA(cudaStreamSynchronize(st));
+    const int64_t Dw = ix->Dw = tails[0], Ds = ix->Ds = tails[1], G = ix->G = tails[2];
+    if (Dw < 0 || Ds < 0 || G < 0 || Dw >= ((int64_t)1 << 27) || Ds >= ((int64_t)1 << 27) || G >= ((int64_t)1 << 31)) {
+        set_error("orie_index_build: row counts out of range (weak %lld, strong %lld, labels %lld; limit 2^27-1 detections per detector)",
+                  (long long)Dw, (long long)Ds, (long long)G);
+        return ORIE_ELIMIT;
+    }
+    const int64_t Dmax = std::max(std::max(Dw, Ds), std::max<int64_t>(G, 1));
+
+    ORIE_TRY(B.keep(&ix->w_off, M + 1));
+    ORIE_TRY(B.keep(&ix->s_off, M + 1));
+    ORIE_CUDA(cudaMemcpyAsync(ix->w_off, w_off, (size_t)(M + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    ORIE_CUDA(cudaMemcpyAsync(ix->s_off, s_off, (size_t)(M + 1) * 8, cudaMemcpyDeviceToDevice, st));
+
+    // ---- temporaries
+    uint64_t *keys, *keys_tmp;
+    uint32_t *vals, *vals_tmp, *img_w, *img_s, *img_l, *order_w, *order_s, *hist, *prank, *q_s, *ownpos, *evcnt;
+    uint16_t *slot_tp;
+    double *conf_sorted;
+    int32_t *status;
+    void *rscratch;
+    ORIE_TRY(B.temp(&keys, Dmax));
+    ORIE_TRY(B.temp(&keys_tmp, Dmax));
+    ORIE_TRY(B.temp(&vals, Dmax));
+    ORIE_TRY(B.temp(&vals_tmp, Dmax));
+    ORIE_TRY(B.temp(&img_w, Dw));
+    ORIE_TRY(B.temp(&img_s, Ds));
+    ORIE_TRY(B.temp(&img_l, G));
+    ORIE_TRY(B.temp(&order_w, Dw));
+    ORIE_TRY(B.temp(&order_s, Ds));
+    ORIE_TRY(B.temp(&hist, 3 * C));
+    ORIE_TRY(B.temp(&prank, Dw));
+    ORIE_TRY(B.temp(&q_s, Ds));
+    ORIE_TRY(B.temp(&ownpos, std::max(Dw, Ds)));
+    ORIE_TRY(B.temp(&conf_sorted, Dw));
+    ORIE_TRY(B.temp(&status, 1));
+    {
+        char *p;
+        ORIE_TRY(B.temp(&p, (int64_t)radix_scratch_bytes(Dmax)));
+        rscratch = p;
+    }
+    ORIE_CUDA(cudaMemsetAsync(status, 0, 4, st));
+    ORIE_CUDA(cudaMemsetAsync(hist, 0, (size_t)(3 * C) * 4, st));
+
+    const int cbits = bits_for(C), ibits = bits_for(M), bbits = bits_for(ix->nbatch);
+
+    // ---- image of every row; class histograms
+    if (Dw) image_of_row_kernel<<<grid_for(Dw), 256, 0, st>>>(w_off, M, Dw, img_w, status);
+    if (Ds) image_of_row_kernel<<<grid_for(Ds), 256, 0, st>>>(s_off, M, Ds, img_s, status);
+    if (G) image_of_row_kernel<<<grid_for(G), 256, 0, st>>>(l_off, M, G, img_l, status);
+    if (Dw) class_hist_kernel<<<grid_for(Dw), 256, 0, st>>>(w_cls, Dw, C, hist, status);
+    if (G) class_hist_kernel<<<grid_for(G), 256, 0, st>>>(l_cls, G, C, hist + C, status);
+    if (Ds) class_hist_kernel<<<grid_for(Ds), 256, 0, st>>>(s_cls, Ds, C, hist + 2 * C, status);  // range check
+    ORIE_LAUNCH_CHECK();
+
+    // ---- global weak order: confidence desc (64-bit key), then class (stable)
+    if (Dw) {
+        conf_keys_kernel<<<grid_for(Dw), 256, 0, st>>>(w_conf, Dw, keys, vals);
+        ORIE_LAUNCH_CHECK();
+        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, Dw, 0, 64, rscratch, st));
+        gather_keys_kernel<<<grid_for(Dw), 256, 0, st>>>((const uint32_t *)w_cls, vals, Dw, 0, keys);
+        ORIE_LAUNCH_CHECK();
+        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, Dw, 0, cbits, rscratch, st));
+        ORIE_CUDA(cudaMemcpyAsync(order_w, vals, (size_t)Dw * 4, cudaMemcpyDeviceToDevice, st));
+    }
+
+    // ---- host: class counts -> padded layouts and segment tables
+    std::vector<uint32_t> h_hist(2 * C);
+    int32_t h_status = 0;
+    ORIE_CUDA(cudaMemcpyAsync(h_hist.data(), hist, (size_t)(2 * C) * 4, cudaMemcpyDeviceToHost, st));
+    ORIE_CUDA(cudaMemcpyAsync(&h_status, status, 4, cudaMemcpyDeviceToHost, st));
+    ORIE_CUDA(cudaStreamSynchronize(st));
+    if (h_status & 2) {
+        set_error("orie_index_build: class id outside [0, %lld)", (long long)C);
+        return ORIE_EDATA;
+    }
+    if (h_status & 1) {
+        set_error("orie_index_build: an image has more than 65535 rows in one file");
+        return ORIE_ELIMIT;
+    }
+    int64_t raw_chunks = 0;
+    for (int64_t c = 0; c < C; ++c) raw_chunks += ceil_div((int64_t)h_hist[c] + 1, kChunk);
+    int seg_chunks = seg_chunks_req > 0 ? seg_chunks_req : (int)std::max<int64_t>(16, ceil_div(raw_chunks, 4096));
+    ix->seg_chunks = seg_chunks;
+    StreamLayout LD = make_layout(h_hist.data(), C, 1, seg_chunks);
+    StreamLayout LL = make_layout(h_hist.data() + C, C, 0, seg_chunks);
+    ix->P = LD.P; ix->nchunks = LD.P / kChunk; ix->S = (int64_t)LD.seg_chunk0.size();
+    ix->PL = LL.P; ix->nchunksL = LL.P / kChunk; ix->SL = (int64_t)LL.seg_chunk0.size();
+    if (ix->P >= ((int64_t)1 << 31)) {
+        set_error("orie_index_build: %lld slots exceed 2^31-1", (long long)ix->P);
+        return ORIE_ELIMIT;
+    }
+    uint32_t *d_cls_off, *d_pad_off, *d_lcls_off, *d_lpad_off;
+    ORIE_TRY(upload(B, &d_cls_off, LD.cls_off, false));
+    ORIE_TRY(upload(B, &d_pad_off, LD.pad_off, false));
+    ORIE_TRY(upload(B, &d_lcls_off, LL.cls_off, false));
+    ORIE_TRY(upload(B, &d_lpad_off, LL.pad_off, false));
+    ORIE_TRY(upload(B, &ix->seg_chunk0, LD.seg_chunk0, true));
+    ORIE_TRY(upload(B, &ix->seg_nch, LD.seg_nch, true));
+    ORIE_TRY(upload(B, &ix->cls_seg0, LD.cls_seg0, true));
+    ORIE_TRY(upload(B, &ix->lseg_chunk0, LL.seg_chunk0, true));
+    ORIE_TRY(upload(B, &ix->lseg_nch, LL.seg_nch, true));
+    ORIE_TRY(upload(B, &ix->lcls_seg0, LL.cls_seg0, true));
+    // the vectors must outlive the async copies
+    ORIE_CUDA(cudaStreamSynchronize(st));
+
+    // ---- slots
+    ORIE_TRY(B.keep(&ix->slot_img, ix->P));
+    ORIE_TRY(B.temp(&slot_tp, ix->P));
+    ORIE_TRY(B.temp(&evcnt, ix->nchunks));
+    ORIE_TRY(B.keep(&ix->evbits, ix->nchunks));
+    ORIE_TRY(B.keep(&ix->evbase, ix->nchunks));
+    ORIE_TRY(B.keep(&ix->seg_ev0, ix->S));
+    fill_u32_kernel<<<grid_for(ix->P), 256, 0, st>>>(ix->slot_img, ix->P, (uint32_t)M);
+    ORIE_CUDA(cudaMemsetAsync(slot_tp, 0, (size_t)ix->P * 2, st));
+    if (Dw)
+        place_slots_kernel<<<grid_for(Dw), 256, 0, st>>>(order_w, w_cls, img_w, w_tp, w_conf, Dw, d_cls_off, d_pad_off,
+                                                       ix->slot_img, slot_tp, prank, conf_sorted);
+    ORIE_LAUNCH_CHECK();
+
+    // ---- events
+    uint32_t *d_total;
+    ORIE_TRY(B.temp(&d_total, 1));
+    event_bits_kernel<<<grid_for(ix->nchunks * 32), 256, 0, st>>>(slot_tp, ix->nchunks, ix->evbits, evcnt);
+    ORIE_LAUNCH_CHECK();
+    {
+        char *sscr;
+        ORIE_TRY(B.temp(&sscr, (int64_t)scan_scratch_bytes(ix->nchunks)));
+        ORIE_TRY(exclusive_scan_u32(evcnt, ix->evbase, ix->nchunks, d_total, sscr, st));
+    }
+    uint32_t h_total = 0;
+    ORIE_CUDA(cudaMemcpyAsync(&h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
+    ORIE_CUDA(cudaStreamSynchronize(st));
+    ix->Ev = h_total;
+    ORIE_TRY(B.keep(&ix->evmask, ix->Ev));
+    event_mask_kernel<<<grid_for(ix->nchunks * 32), 256, 0, st>>>(slot_tp, ix->nchunks, ix->evbits, ix->evbase, ix->evmask);
+    gather_seg_ev0_kernel<<<grid_for(ix->S), 256, 0, st>>>(ix->seg_chunk0, ix->S, ix->evbase, ix->seg_ev0);
+    ORIE_LAUNCH_CHECK();
+
+    // ---- strong: insertion slots, global (class, conf desc) order
+    if (Ds) {
+        strong_query_kernel<<<grid_for(Ds), 256, 0, st>>>(s_cls, s_conf, Ds, conf_sorted, d_cls_off, d_pad_off, q_s);
+        conf_keys_kernel<<<grid_for(Ds), 256, 0, st>>>(s_conf, Ds, keys, vals);
+        ORIE_LAUNCH_CHECK();
+        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, Ds, 0, 64, rscratch, st));
+        gather_keys_kernel<<<grid_for(Ds), 256, 0, st>>>((const uint32_t *)s_cls, vals, Ds, 0, keys);
+        ORIE_LAUNCH_CHECK();
+        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, Ds, 0, cbits, rscratch, st));
+        ORIE_CUDA(cudaMemcpyAsync(order_s, vals, (size_t)Ds * 4, cudaMemcpyDeviceToDevice, st));
+    }
+
+    // ---- own lists and batch query lists, both detectors
+    ORIE_TRY(B.keep(&ix->own_w_q, Dw));
+    ORIE_TRY(B.keep(&ix->own_w_m, Dw));
+    ORIE_TRY(B.keep(&ix->own_s_q, Ds));
+    ORIE_TRY(B.keep(&ix->own_s_m, Ds));
+    ORIE_TRY(B.keep(&ix->own_w_cs, M * (C + 1)));
+    ORIE_TRY(B.keep(&ix->own_s_cs, M * (C + 1)));
+    ORIE_TRY(B.keep(&ix->bq_w, Dw));
+    ORIE_TRY(B.keep(&ix->bq_s, Ds));
+    ORIE_TRY(B.keep(&ix->bqoff_w, ix->nbatch * (ix->S + 1)));
+    ORIE_TRY(B.keep(&ix->bqoff_s, ix->nbatch * (ix->S + 1)));
+    ORIE_CUDA(cudaMemsetAsync(ix->own_w_cs, 0, (size_t)(M * (C + 1)) * 2, st));
+    ORIE_CUDA(cudaMemsetAsync(ix->own_s_cs, 0, (size_t)(M * (C + 1)) * 2, st));
+    struct Det {
+        int64_t n;
+        const uint32_t *order, *img, *q;
+        const int32_t *cls;
+        const uint16_t *tp;
+        const int64_t *off;
+        uint32_t *own_q;
+        uint16_t *own_m, *own_cs;
+        uint2 *bq;
+        uint32_t *bqoff;
+    } dets[2] = {{Dw, order_w, img_w, prank, w_cls, w_tp, ix->w_off, ix->own_w_q, ix->own_w_m, ix->own_w_cs, ix->bq_w, ix->bqoff_w},
+                 {Ds, order_s, img_s, q_s, s_cls, s_tp, ix->s_off, ix->own_s_q, ix->own_s_m, ix->own_s_cs, ix->bq_s, ix->bqoff_s}};
+    for (const Det &d : dets) {
+        if (d.n) {
+            // image-major: stable sort of the global order by image
+            ORIE_CUDA(cudaMemcpyAsync(vals, d.order, (size_t)d.n * 4, cudaMemcpyDeviceToDevice, st));
+            gather_keys_kernel<<<grid_for(d.n), 256, 0, st>>>(d.img, vals, d.n, 0, keys);
+            ORIE_LAUNCH_CHECK();
+            ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, d.n, 0, ibits, rscratch, st));
+            own_fill_kernel<<<grid_for(d.n), 256, 0, st>>>(vals, d.n, d.q, d.tp, d.own_q, d.own_m, ownpos);
+            own_class_start_kernel<<<grid_for(d.n), 256, 0, st>>>(vals, d.n, d.cls, d.img, d.off, C, d.own_cs);
+            ORIE_LAUNCH_CHECK();
+            // batch-major: stable sort of the global order by image / 32
+            ORIE_CUDA(cudaMemcpyAsync(vals, d.order, (size_t)d.n * 4, cudaMemcpyDeviceToDevice, st));
+            gather_keys_kernel<<<grid_for(d.n), 256, 0, st>>>(d.img, vals, d.n, 5, keys);
+            ORIE_LAUNCH_CHECK();
+            ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, d.n, 0, bbits, rscratch, st));
+            batch_query_kernel<<<grid_for(d.n), 256, 0, st>>>(vals, d.n, d.q, d.img, ownpos, d.bq);
+            ORIE_LAUNCH_CHECK();
+        }
+        batch_query_offsets_kernel<<<grid_for(ix->nbatch * (ix->S + 1)), 256, 0, st>>>(d.bq, d.off, M, ix->nbatch,
+                                                                                     ix->seg_chunk0, ix->S, d.bqoff);
+        ORIE_LAUNCH_CHECK();
+    }
+
+    // ---- label stream
+    ORIE_TRY(B.keep(&ix->lab_slot_img, ix->PL));
+    ORIE_TRY(B.keep(&ix->gtcnt, M * C));
+    ORIE_CUDA(cudaMemsetAsync(ix->gtcnt, 0, (size_t)(M * C) * 4, st));
+    if (ix->PL) fill_u32_kernel<<<grid_for(ix->PL), 256, 0, st>>>(ix->lab_slot_img, ix->PL, (uint32_t)M);
+    if (G) {
+        label_keys_kernel<<<grid_for(G), 256, 0, st>>>(l_cls, img_l, G, C, keys, vals, ix->gtcnt);
+        ORIE_LAUNCH_CHECK();
+        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, G, 0, cbits, rscratch, st));
+        place_labels_kernel<<<grid_for(G), 256, 0, st>>>(keys, vals, G, d_lcls_off, d_lpad_off, ix->lab_slot_img);
+    }
+    ORIE_LAUNCH_CHECK();
+    ORIE_CUDA(cudaStreamSynchronize(st));
+    return ORIE_OK;
+}
+
+}  // namespace orie
+
+using namespace orie;
+
+extern "C" int orie_index_build(int64_t M, int64_t C, int T,
+                                const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
+                                const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
+                                const int64_t *l_off, const int32_t *l_cls, int seg_chunks, orie_stream_t stream,
+                                orie_index_t **out) {
+    if (!out) {
+        set_error("orie_index_build: out is NULL");
+        return ORIE_EINVAL;
+    }
+    *out = nullptr;
+    if (M < 1 || C < 1 || !w_off || !s_off || !l_off) {
+        set_error("orie_index_build: need M >= 1, C >= 1 and the three offset arrays");
+        return ORIE_EINVAL;
+    }
+    if (T < 1 || T > ORIE_MAX_THRESHOLDS) {
+        set_error("orie_index_build: T=%d outside [1,%d]", T, ORIE_MAX_THRESHOLDS);
+        return ORIE_ELIMIT;
+    }
+    if (M >= ((int64_t)1 << 27) || C > 65535) {
+        set_error("orie_index_build: M=%lld or C=%lld exceeds the engine limits (2^27-1 images, 65535 classes)",
+                  (long long)M, (long long)C);
+        return ORIE_ELIMIT;
+    }
+    orie_index *ix = new orie_index();
+    ix->M = M; ix->C = C; ix->T = T;
+    ix->nbatch = ceil_div(M, 32);
+    ix->ens_words = ceil_div(M + 1, 32);
+    ix->cls_per_warp = 32 / T;
+    ix->class_groups = ceil_div(C, ix->cls_per_warp);
+    int rc = build(ix, w_off, w_cls, w_conf, w_tp, s_off, s_cls, s_conf, s_tp, l_off, l_cls, seg_chunks, stream);
+    if (rc != ORIE_OK) {
+        orie_index_destroy(ix);
+        return rc;
+    }
+    *out = ix;
+    return ORIE_OK;
+}
+
+extern "C" void orie_index_destroy(orie_index_t *ix) {
+    if (!ix) return;
+    for (int i = 0; i < ix->n_allocs; ++i) cudaFree(ix->allocs[i]);
+    delete ix;
+}
+
+extern "C" int orie_index_info(const orie_index_t *ix, orie_index_info_t *info) {
+    if (!ix || !info) {
+        set_error("orie_index_info: null argument");
+        return ORIE_EINVAL;
+    }
+    info->num_images = ix->M; info->num_classes = ix->C;
+    info->num_thresholds = ix->T; info->seg_chunks = ix->seg_chunks;
+    info->num_weak = ix->Dw; info->num_strong = ix->Ds; info->num_labels = ix->G;
+    info->slots = ix->P; info->segments = ix->S; info->events = ix->Ev;
+    info->label_slots = ix->PL; info->label_segments = ix->SL;
+    info->class_groups = ix->class_groups;
+    info->ens_words = ix->ens_words;
+    info->device_bytes = ix->device_bytes;
+    return ORIE_OK;
+}

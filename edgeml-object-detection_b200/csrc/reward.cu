@@ -1,0 +1,558 @@
+// ORIE reward pass (orie_reward) and ensemble construction.
+//
+// Replaces reward.py:16-52 (compute_orie), lib/metrics.py:89-124 (ap_per_class)
+// and :127-148 (compute_ap) without re-sorting or re-matching anything per target.
+//
+//   K1  walk_kernel      32 targets at a time (one per lane).  A warp streams a segment of
+//                        the class-sorted slot array, looks every slot's image up in a
+//                        shared-memory table of 32-target membership words, transposes the
+//                        32x32 bit block with 5 shuffles so lane j holds target j's membership
+//                        word, and keeps per-target running ranks with popc.  It emits, per
+//                        target: members per segment, the rank of every member true positive
+//                        ("event"), and the rank of the target's own detections.
+//   K2  ap_kernel        one warp per (target, group of 32/T classes); lane = (class, IoU
+//                        threshold).  A single reverse sweep over the events integrates the
+//                        101-point interpolated AP exactly as compute_ap does (precision
+//                        envelope = running max in reverse, np.interp's "last knot <= x" rule,
+//                        np.trapz), for the weak and the strong variant side by side.
+//   K3  finalize_kernel  (N+1) * (mean strong AP - mean weak AP), NaN -> 0 (reward.py:50,86).
+//
+// All arithmetic that decides a branch or a reward digit is IEEE float64 in upstream's order
+// (explicit _rn intrinsics; the library is built with -fmad=false).
+#include "index.cuh"
+
+namespace orie {
+
+// ----------------------------------------------------------------------------
+// 32x32 bit-matrix transpose across a warp: in  = row `lane`, bit c = column c
+//                                            out = column `lane`, bit r = row r
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(kFull, x, s);
+        x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
+    }
+    return x;
+}
+
+// ----------------------------------------------------------------------------
+// ensembles
+// ----------------------------------------------------------------------------
+__global__ void ens_from_indices_kernel(const int32_t *__restrict__ ens_idx, int64_t nt, int64_t N, int64_t t0, int64_t M,
+                                        int64_t words, uint32_t *__restrict__ bits, int32_t *__restrict__ status) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nt * N) return;
+    const int64_t r = k / N;
+    const int64_t e = ens_idx[k];
+    if (e < 0 || e >= M || e == t0 + r) { atomicOr(status, 1); return; }
+    const uint32_t bit = 1u << (e & 31);
+    const uint32_t old = atomicOr(&bits[r * words + (e >> 5)], bit);
+    if (old & bit) atomicOr(status, 2);
+}
+
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so a target's ensemble depends only on
+// (seed, target) — not on the launch shape or on how targets are sharded over GPUs.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+// One warp per target.  Draws `want` distinct images != target into the target's bitmap
+// (32 candidates per round, duplicates inside a round resolved by lane order, quota cut in lane
+// order), then complements the bitmap when the ensemble is more than half of the dataset.
+__global__ void ens_sample_kernel(int64_t nt, int64_t N, int64_t t0, int64_t M, int64_t words, uint64_t seed,
+                                  uint32_t *__restrict__ bits_all) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= nt) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t target = t0 + r;
+    uint32_t *bits = bits_all + r * words;
+    const int64_t others = M - 1;
+    const bool complement = 2 * N > others;
+    const int64_t want = complement ? others - N : N;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    int64_t have = 0;
+    for (uint32_t round = 0; have < want; ++round) {
+        const uint4 rnd = philox4x32(make_uint4((uint32_t)target, (uint32_t)(target >> 32), round, (uint32_t)lane), key);
+        const uint64_t r64 = ((uint64_t)rnd.x << 32) | rnd.y;
+        int64_t e = (int64_t)__umul64hi(r64, (uint64_t)others);   // uniform in [0, others)
+        e += (e >= target);
+        const unsigned peers = __match_any_sync(kFull, e);
+        bool ok = lane == (__ffs(peers) - 1);
+        const uint32_t bit = 1u << (e & 31);
+        if (ok) ok = !(*(volatile uint32_t *)&bits[e >> 5] & bit);
+        const unsigned acc = __ballot_sync(kFull, ok);
+        const int before = __popc(acc & ((1u << lane) - 1u));
+        if (ok && have + before < want) atomicOr(&bits[e >> 5], bit);
+        __syncwarp();
+        have += __popc(acc);
+    }
+    if (complement) {
+        __syncwarp();
+        for (int64_t w = lane; w < words; w += 32) {
+            uint32_t v = ~*(volatile uint32_t *)&bits[w];
+            const int64_t lo = w * 32;
+            if (lo + 32 > M) v &= (M > lo) ? ((M - lo >= 32) ? 0xffffffffu : ((1u << (M - lo)) - 1u)) : 0u;
+            if ((target >> 5) == w) v &= ~(1u << (target & 31));
+            bits[w] = v;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// K1: walk
+// ----------------------------------------------------------------------------
+struct WalkParams {
+    int64_t M, nt, ntp, t0;
+    int64_t ens_words;
+    const uint32_t *ens_bits;   // [nt][ens_words]
+    // stream
+    const uint32_t *slot_img;
+    const int32_t *seg_chunk0, *seg_nch;
+    int64_t S;
+    int segs_per_block;
+    uint32_t *tot;              // [S][ntp]
+    // detection stream only
+    const uint32_t *evbits;
+    const uint16_t *evmask;
+    const uint32_t *seg_ev0;
+    const uint2 *bq_w, *bq_s;
+    const uint32_t *bqoff_w, *bqoff_s;   // [nbatch][S+1]
+    int64_t Ev;
+    uint32_t *evcnt;            // [S][ntp]
+    uint64_t *ev;               // [ntp][Ev]
+    uint32_t *cb_w, *cb_s;
+};
+
+constexpr int kWalkMaxThreads = 1024;
+
+template <bool DETS>
+__global__ void __launch_bounds__(kWalkMaxThreads)
+walk_kernel(const WalkParams p) {
+    extern __shared__ uint32_t memb[];   // [ens_words * 32]: bit j of memb[img] = img in ensemble of target 32*batch+j
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kWarps = blockDim.x >> 5;
+    const int64_t lb = blockIdx.x;                 // local batch
+    const int64_t tl = lb * 32 + lane;             // local target of this lane
+    {
+        const uint32_t *row = p.ens_bits + tl * p.ens_words;
+        const bool live = tl < p.nt;
+        for (int64_t w = warp; w < p.ens_words; w += kWarps) {
+            const uint32_t x = live ? row[w] : 0u;
+            memb[w * 32 + lane] = transpose32(x, lane);
+        }
+    }
+    __syncthreads();
+    const int64_t gb = (p.t0 >> 5) + lb;           // global batch (query lists are per global batch)
+    const int64_t sbeg = (int64_t)blockIdx.y * p.segs_per_block;
+    const int64_t send = min(sbeg + p.segs_per_block, p.S);
+    for (int64_t s = sbeg + warp; s < send; s += kWarps) {
+        const int64_t ch0 = p.seg_chunk0[s];
+        const int nch = p.seg_nch[s];
+        uint32_t cnt = 0, ecur = 0;
+        uint32_t ev_i = 0, qw = 0, qw_end = 0, qs = 0, qs_end = 0;
+        uint2 nqw = make_uint2(0xffffffffu, 0u), nqs = make_uint2(0xffffffffu, 0u);
+        uint64_t *evout = nullptr;
+        if (DETS) {
+            ev_i = p.seg_ev0[s];
+            evout = p.ev + tl * p.Ev + ev_i;
+            const uint32_t *ow = p.bqoff_w + gb * (p.S + 1) + s;
+            const uint32_t *os = p.bqoff_s + gb * (p.S + 1) + s;
+            qw = ow[0]; qw_end = ow[1];
+            qs = os[0]; qs_end = os[1];
+            if (qw < qw_end) nqw = p.bq_w[qw];
+            if (qs < qs_end) nqs = p.bq_s[qs];
+        }
+        for (int c = 0; c < nch; ++c) {
+            const int64_t ch = ch0 + c;
+            const uint32_t img = p.slot_img[ch * 32 + lane];
+            const uint32_t word = transpose32(memb[img], lane);   // bit l: slot l holds a member of MY target
+            if (DETS) {
+                uint32_t eb = p.evbits[ch];
+                while (eb) {
+                    const int b = __ffs(eb) - 1;
+                    eb &= eb - 1;
+                    const uint32_t mask = p.evmask[ev_i++];
+                    if ((word >> b) & 1u) {
+                        const uint32_t rank = cnt + __popc(word & ((2u << b) - 1u));   // 1-based, inclusive
+                        evout[ecur++] = (uint64_t)rank | ((uint64_t)mask << 32);
+                    }
+                }
+                const uint32_t chunk_end = (uint32_t)(ch + 1) * 32u;
+                while (nqw.x < chunk_end) {                     // uniform: own weak detections in this chunk
+                    if (lane == (int)(nqw.y >> 27))
+                        p.cb_w[nqw.y & 0x07ffffffu] = cnt + __popc(word & ((1u << (nqw.x & 31u)) - 1u));
+                    ++qw;
+                    nqw = qw < qw_end ? p.bq_w[qw] : make_uint2(0xffffffffu, 0u);
+                }
+                while (nqs.x < chunk_end) {                     // uniform: own strong detections inserted here
+                    if (lane == (int)(nqs.y >> 27))
+                        p.cb_s[nqs.y & 0x07ffffffu] = cnt + __popc(word & ((1u << (nqs.x & 31u)) - 1u));
+                    ++qs;
+                    nqs = qs < qs_end ? p.bq_s[qs] : make_uint2(0xffffffffu, 0u);
+                }
+            }
+            cnt += __popc(word);
+        }
+        p.tot[s * p.ntp + tl] = cnt;
+        if (DETS) p.evcnt[s * p.ntp + tl] = ecur;
+    }
+}
+
+// ----------------------------------------------------------------------------
+// K2: AP integration
+// ----------------------------------------------------------------------------
+struct Grid101 {
+    double x[101];   // np.linspace(0, 1, 101)
+    double d[100];   // np.diff(x)
+};
+
+struct ApParams {
+    int64_t M, C, nt, ntp, t0;
+    int T, cls_per_warp;
+    int64_t class_groups;
+    int64_t S, SL, Ev;
+    const int32_t *cls_seg0, *seg_chunk0, *lcls_seg0;
+    const uint32_t *seg_ev0;
+    const uint32_t *tot, *evcnt, *totL;
+    const uint64_t *ev;
+    const uint32_t *gtcnt;
+    const int64_t *w_off, *s_off;
+    const uint16_t *own_w_cs, *own_s_cs, *own_w_m, *own_s_m;
+    const uint32_t *own_w_q, *own_s_q, *cb_w, *cb_s;
+    double *partial;    // [ntp][class_groups][3]
+};
+
+// Reverse-sweep state of one (class, threshold, variant) integral; see oracle/event_model.py:_Var.
+struct ApVar {
+    double ap, y_next, E, r_cur, n_l;
+    int g, k;
+    bool dead;
+
+    __device__ __forceinline__ void consume(const double *gx, const double *gd, double r_lo, double env_lo, double r_hi,
+                                            double env_hi) {
+        if (g >= 0 && gx[g] >= r_lo) {
+            const double slope = __ddiv_rn(__dsub_rn(env_hi, env_lo), __dsub_rn(r_hi, r_lo));
+            do {
+                const double x = gx[g];
+                const double y = (x == r_lo) ? env_lo : __dadd_rn(__dmul_rn(slope, __dsub_rn(x, r_lo)), env_lo);
+                ap = __dadd_rn(ap, __ddiv_rn(__dmul_rn(gd[g], __dadd_rn(y_next, y)), 2.0));
+                y_next = y;
+                --g;
+            } while (g >= 0 && gx[g] >= r_lo);
+        }
+    }
+    __device__ __forceinline__ void init(const double *gx, const double *gd, int K, int64_t n_p, uint32_t nl) {
+        ap = 0.0; y_next = 0.0; E = -1.0; g = 99; k = K; n_l = (double)nl; r_cur = 0.0;
+        dead = (K == 0 || n_p == 0);
+        if (dead) return;
+        const double r_k = __ddiv_rn((double)K, n_l);
+        consume(gx, gd, r_k, __ddiv_rn((double)K, (double)n_p), 1.0, 0.0);
+        r_cur = r_k;
+    }
+    // the k-th true positive (k = current k) sits at 1-based rank pos
+    __device__ __forceinline__ void step(const double *gx, const double *gd, int64_t pos) {
+        if (dead) return;
+        E = fmax(E, __ddiv_rn((double)k, (double)pos));
+        const double r_lo = __ddiv_rn((double)(k - 1), n_l);
+        const int64_t j = pos - 1;
+        const double prec_j = j == 0 ? 1.0 : __ddiv_rn((double)(k - 1), (double)j);
+        consume(gx, gd, r_lo, fmax(prec_j, E), r_cur, E);
+        r_cur = r_lo;
+        --k;
+    }
+};
+
+constexpr int kApThreads = 128;
+
+__global__ void __launch_bounds__(kApThreads)
+ap_kernel(const ApParams p, const Grid101 grid) {
+    __shared__ double gx[101];
+    __shared__ double gd[100];
+    for (int i = threadIdx.x; i < 101; i += kApThreads) gx[i] = grid.x[i];
+    for (int i = threadIdx.x; i < 100; i += kApThreads) gd[i] = grid.d[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * (kApThreads / 32) + (threadIdx.x >> 5);
+    if (item >= p.nt * p.class_groups) return;
+    const int64_t tl = item / p.class_groups, grp = item % p.class_groups;
+    const int slot = lane / p.T, t = lane % p.T;
+    const int64_t c = grp * p.cls_per_warp + slot;
+    const bool active = slot < p.cls_per_warp && c < p.C;
+    const int64_t j = p.t0 + tl;
+
+    double ap_w = 0.0, ap_s = 0.0, has_gt = 0.0;
+    if (active) {
+        uint32_t n_l = p.gtcnt[j * p.C + c];
+        for (int ls = p.lcls_seg0[c]; ls < p.lcls_seg0[c + 1]; ++ls) n_l += p.totL[(int64_t)ls * p.ntp + tl];
+        if (n_l > 0) {
+            if (t == 0) has_gt = 1.0;
+            const int s0 = p.cls_seg0[c], s1 = p.cls_seg0[c + 1];
+            const uint64_t *ev = p.ev + tl * p.Ev;
+            int64_t n_ens = 0;
+            int K_ens = 0;
+            for (int s = s0; s < s1; ++s) {
+                n_ens += p.tot[(int64_t)s * p.ntp + tl];
+                const uint64_t *e = ev + p.seg_ev0[s];
+                const int ne = (int)p.evcnt[(int64_t)s * p.ntp + tl];
+                for (int i = 0; i < ne; ++i) K_ens += (int)((e[i] >> (32 + t)) & 1ull);
+            }
+            const int64_t wa = p.w_off[j] + p.own_w_cs[j * (p.C + 1) + c], wb = p.w_off[j] + p.own_w_cs[j * (p.C + 1) + c + 1];
+            const int64_t sa = p.s_off[j] + p.own_s_cs[j * (p.C + 1) + c], sb = p.s_off[j] + p.own_s_cs[j * (p.C + 1) + c + 1];
+            int K_w = K_ens, K_s = K_ens;
+            for (int64_t i = wa; i < wb; ++i) K_w += (p.own_w_m[i] >> t) & 1;
+            for (int64_t i = sa; i < sb; ++i) K_s += (p.own_s_m[i] >> t) & 1;
+            ApVar vw, vs;
+            vw.init(gx, gd, K_w, n_ens + (wb - wa), n_l);
+            vs.init(gx, gd, K_s, n_ens + (sb - sa), n_l);
+            if (!(vw.dead && vs.dead)) {
+                int64_t ibw = wb - 1, ibs = sb - 1;
+                int64_t rem = n_ens;
+                for (int s = s1 - 1; s >= s0; --s) {
+                    rem -= p.tot[(int64_t)s * p.ntp + tl];
+                    const int64_t base = rem;
+                    const uint32_t slot0 = (uint32_t)p.seg_chunk0[s] * 32u;
+                    const uint64_t *e = ev + p.seg_ev0[s];
+                    const int ne = (int)p.evcnt[(int64_t)s * p.ntp + tl];
+                    for (int i = ne - 1; i >= 0; --i) {
+                        const uint64_t rec = e[i];
+                        const int64_t pos = base + (int64_t)(uint32_t)rec;
+                        while (ibw >= wa && p.own_w_q[ibw] >= slot0 && base + (int64_t)p.cb_w[ibw] >= pos) {
+                            if ((p.own_w_m[ibw] >> t) & 1) vw.step(gx, gd, base + (int64_t)p.cb_w[ibw] + 1 + (ibw - wa));
+                            --ibw;
+                        }
+                        while (ibs >= sa && p.own_s_q[ibs] >= slot0 && base + (int64_t)p.cb_s[ibs] >= pos) {
+                            if ((p.own_s_m[ibs] >> t) & 1) vs.step(gx, gd, base + (int64_t)p.cb_s[ibs] + 1 + (ibs - sa));
+                            --ibs;
+                        }
+                        if ((rec >> (32 + t)) & 1ull) {
+                            vw.step(gx, gd, pos + (ibw - wa + 1));
+                            vs.step(gx, gd, pos + (ibs - sa + 1));
+                        }
+                    }
+                    while (ibw >= wa && p.own_w_q[ibw] >= slot0) {
+                        if ((p.own_w_m[ibw] >> t) & 1) vw.step(gx, gd, base + (int64_t)p.cb_w[ibw] + 1 + (ibw - wa));
+                        --ibw;
+                    }
+                    while (ibs >= sa && p.own_s_q[ibs] >= slot0) {
+                        if ((p.own_s_m[ibs] >> t) & 1) vs.step(gx, gd, base + (int64_t)p.cb_s[ibs] + 1 + (ibs - sa));
+                        --ibs;
+                    }
+                }
+            }
+            ap_w = vw.dead ? 0.0 : vw.ap;
+            ap_s = vs.dead ? 0.0 : vs.ap;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        ap_w = __dadd_rn(ap_w, __shfl_xor_sync(kFull, ap_w, d));
+        ap_s = __dadd_rn(ap_s, __shfl_xor_sync(kFull, ap_s, d));
+        has_gt += __shfl_xor_sync(kFull, has_gt, d);
+    }
+    if (lane == 0) {
+        double *out = p.partial + (tl * p.class_groups + grp) * 3;
+        out[0] = ap_w; out[1] = ap_s; out[2] = has_gt;
+    }
+}
+
+// ----------------------------------------------------------------------------
+// K3
+// ----------------------------------------------------------------------------
+__global__ void finalize_kernel(const double *__restrict__ partial, int64_t nt, int64_t groups, int T, int64_t N,
+                                double *__restrict__ reward, double *__restrict__ detail) {
+    const int64_t tl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tl >= nt) return;
+    double sw = 0.0, ss = 0.0, nc = 0.0;
+    for (int64_t g = 0; g < groups; ++g) {
+        const double *q = partial + (tl * groups + g) * 3;
+        sw = __dadd_rn(sw, q[0]);
+        ss = __dadd_rn(ss, q[1]);
+        nc += q[2];
+    }
+    double r = 0.0;
+    if (nc > 0.0) {
+        const double cnt = nc * (double)T;
+        r = __dmul_rn(__dsub_rn(__ddiv_rn(ss, cnt), __ddiv_rn(sw, cnt)), (double)(N + 1));
+    }
+    reward[tl] = r;   // nc == 0: upstream's mean over an empty AP table is NaN, stored as 0 (reward.py:86)
+    if (detail) { detail[tl * 3] = sw; detail[tl * 3 + 1] = ss; detail[tl * 3 + 2] = nc; }
+}
+
+// ----------------------------------------------------------------------------
+// workspace
+// ----------------------------------------------------------------------------
+struct WsLayout {
+    size_t tot, evcnt, totL, ev, cb_w, cb_s, partial, total;
+};
+
+static WsLayout ws_layout(const orie_index *ix, int64_t nt) {
+    const int64_t ntp = round_up(nt, 32);
+    WsLayout L;
+    size_t o = 0;
+    auto take = [&](int64_t bytes) { size_t at = o; o += (size_t)round_up(bytes > 0 ? bytes : 1, 256); return at; };
+    L.tot = take(ix->S * ntp * 4);
+    L.evcnt = take(ix->S * ntp * 4);
+    L.totL = take(ix->SL * ntp * 4);
+    L.ev = take(ntp * ix->Ev * 8);
+    L.cb_w = take(ix->Dw * 4);
+    L.cb_s = take(ix->Ds * 4);
+    L.partial = take(ntp * ix->class_groups * 3 * 8);
+    L.total = o;
+    return L;
+}
+
+}  // namespace orie
+
+using namespace orie;
+
+extern "C" size_t orie_reward_workspace_bytes(const orie_index_t *ix, int64_t nt) {
+    if (!ix || nt < 0) return 0;
+    return ws_layout(ix, nt).total;
+}
+
+static int check_range(const orie_index *ix, int64_t t0, int64_t nt, const char *who) {
+    if (!ix) { set_error("%s: index is NULL", who); return ORIE_EINVAL; }
+    if (t0 < 0 || nt < 0 || t0 + nt > ix->M || (t0 & 31)) {
+        set_error("%s: target range [%lld, %lld) must lie inside [0, %lld) and start at a multiple of 32",
+                  who, (long long)t0, (long long)(t0 + nt), (long long)ix->M);
+        return ORIE_EINVAL;
+    }
+    return ORIE_OK;
+}
+
+extern "C" int orie_ensemble_from_indices(const orie_index_t *ix, int64_t t0, int64_t nt, const int32_t *ens_idx, int64_t N,
+                                          uint32_t *ens_bits, int32_t *status, orie_stream_t stream) {
+    ORIE_TRY(check_range(ix, t0, nt, "orie_ensemble_from_indices"));
+    if (N < 0 || N > ix->M - 1 || !ens_bits || !status || (N > 0 && !ens_idx)) {
+        set_error("orie_ensemble_from_indices: need 0 <= N <= M-1 and non-null buffers");
+        return ORIE_EINVAL;
+    }
+    if (nt == 0) return ORIE_OK;
+    ORIE_CUDA(cudaMemsetAsync(ens_bits, 0, (size_t)(nt * ix->ens_words) * 4, stream));
+    if (N > 0) {
+        const int64_t n = nt * N;
+        ens_from_indices_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(ens_idx, nt, N, t0, ix->M, ix->ens_words,
+                                                                            ens_bits, status);
+        ORIE_LAUNCH_CHECK();
+    }
+    return ORIE_OK;
+}
+
+extern "C" int orie_ensemble_sample(const orie_index_t *ix, int64_t t0, int64_t nt, int64_t N, uint64_t seed,
+                                    uint32_t *ens_bits, orie_stream_t stream) {
+    ORIE_TRY(check_range(ix, t0, nt, "orie_ensemble_sample"));
+    if (N < 0 || N > ix->M - 1 || !ens_bits) {
+        set_error("orie_ensemble_sample: need 0 <= N <= M-1 and a bitmap buffer");
+        return ORIE_EINVAL;
+    }
+    if (nt == 0) return ORIE_OK;
+    ORIE_CUDA(cudaMemsetAsync(ens_bits, 0, (size_t)(nt * ix->ens_words) * 4, stream));
+    ens_sample_kernel<<<(unsigned)ceil_div(nt * 32, 128), 128, 0, stream>>>(nt, N, t0, ix->M, ix->ens_words, seed, ens_bits);
+    ORIE_LAUNCH_CHECK();
+    return ORIE_OK;
+}
+
+extern "C" int orie_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
+                           void *workspace, size_t workspace_bytes, double *reward, double *detail, orie_stream_t stream) {
+    ORIE_TRY(check_range(ix, t0, nt, "orie_reward"));
+    if (!ens_bits || !reward || !workspace || N < 0) {
+        set_error("orie_reward: null buffer or negative N");
+        return ORIE_EINVAL;
+    }
+    if (nt == 0) return ORIE_OK;
+    const WsLayout L = ws_layout(ix, nt);
+    if (workspace_bytes < L.total) {
+        set_error("orie_reward: workspace has %zu bytes, %zu needed for %lld targets", workspace_bytes, L.total, (long long)nt);
+        return ORIE_EWORKSPACE;
+    }
+    if ((uintptr_t)workspace & 255) {
+        set_error("orie_reward: workspace must be 256-byte aligned");
+        return ORIE_EINVAL;
+    }
+    char *ws = (char *)workspace;
+    const int64_t ntp = round_up(nt, 32);
+    const size_t smem = (size_t)ix->ens_words * 32 * 4;
+    if (smem > 227 * 1024) {
+        set_error("orie_reward: %lld images need %zu bytes of shared memory for the membership table (limit %d)",
+                  (long long)ix->M, smem, 227 * 1024);
+        return ORIE_ELIMIT;
+    }
+    static_assert(sizeof(WalkParams) < 4000 && sizeof(ApParams) + sizeof(Grid101) < 4000, "kernel parameter space");
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    WalkParams wp;
+    memset(&wp, 0, sizeof(wp));
+    wp.M = ix->M; wp.nt = nt; wp.ntp = ntp; wp.t0 = t0;
+    wp.ens_words = ix->ens_words; wp.ens_bits = ens_bits;
+    const int64_t nb = ntp / 32;
+    const int walk_threads = smem <= 56 * 1024 ? 256 : smem <= 112 * 1024 ? 512 : 1024;   // keep the SM full of warps
+    auto segs_per_block = [&](int64_t S) {
+        // enough blocks for >= 4 waves of 148 SMs when the data allows, at least one segment per warp
+        int64_t want_y = ceil_div(4 * 148, nb);
+        int64_t spb = ceil_div(S, want_y > 0 ? want_y : 1);
+        const int64_t warps = walk_threads / 32;
+        spb = round_up(spb > 0 ? spb : 1, warps);
+        return (int)spb;
+    };
+    // labels
+    if (ix->SL > 0) {
+        WalkParams lp = wp;
+        lp.slot_img = ix->lab_slot_img; lp.seg_chunk0 = ix->lseg_chunk0; lp.seg_nch = ix->lseg_nch;
+        lp.S = ix->SL; lp.segs_per_block = segs_per_block(ix->SL);
+        lp.tot = (uint32_t *)(ws + L.totL);
+        dim3 grid((unsigned)nb, (unsigned)ceil_div(ix->SL, lp.segs_per_block));
+        walk_kernel<false><<<grid, walk_threads, smem, stream>>>(lp);
+        ORIE_LAUNCH_CHECK();
+    }
+    // detections
+    {
+        wp.slot_img = ix->slot_img; wp.seg_chunk0 = ix->seg_chunk0; wp.seg_nch = ix->seg_nch;
+        wp.S = ix->S; wp.segs_per_block = segs_per_block(ix->S);
+        wp.tot = (uint32_t *)(ws + L.tot);
+        wp.evbits = ix->evbits; wp.evmask = ix->evmask; wp.seg_ev0 = ix->seg_ev0;
+        wp.bq_w = ix->bq_w; wp.bq_s = ix->bq_s; wp.bqoff_w = ix->bqoff_w; wp.bqoff_s = ix->bqoff_s;
+        wp.Ev = ix->Ev;
+        wp.evcnt = (uint32_t *)(ws + L.evcnt);
+        wp.ev = (uint64_t *)(ws + L.ev);
+        wp.cb_w = (uint32_t *)(ws + L.cb_w);
+        wp.cb_s = (uint32_t *)(ws + L.cb_s);
+        dim3 grid((unsigned)nb, (unsigned)ceil_div(ix->S, wp.segs_per_block));
+        walk_kernel<true><<<grid, walk_threads, smem, stream>>>(wp);
+        ORIE_LAUNCH_CHECK();
+    }
+    // AP
+    ApParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.M = ix->M; ap.C = ix->C; ap.nt = nt; ap.ntp = ntp; ap.t0 = t0;
+    ap.T = ix->T; ap.cls_per_warp = ix->cls_per_warp; ap.class_groups = ix->class_groups;
+    ap.S = ix->S; ap.SL = ix->SL; ap.Ev = ix->Ev;
+    ap.cls_seg0 = ix->cls_seg0; ap.seg_chunk0 = ix->seg_chunk0; ap.lcls_seg0 = ix->lcls_seg0; ap.seg_ev0 = ix->seg_ev0;
+    ap.tot = (const uint32_t *)(ws + L.tot); ap.evcnt = (const uint32_t *)(ws + L.evcnt);
+    ap.totL = (const uint32_t *)(ws + L.totL); ap.ev = (const uint64_t *)(ws + L.ev);
+    ap.gtcnt = ix->gtcnt; ap.w_off = ix->w_off; ap.s_off = ix->s_off;
+    ap.own_w_cs = ix->own_w_cs; ap.own_s_cs = ix->own_s_cs; ap.own_w_m = ix->own_w_m; ap.own_s_m = ix->own_s_m;
+    ap.own_w_q = ix->own_w_q; ap.own_s_q = ix->own_s_q;
+    ap.cb_w = (const uint32_t *)(ws + L.cb_w); ap.cb_s = (const uint32_t *)(ws + L.cb_s);
+    ap.partial = (double *)(ws + L.partial);
+    Grid101 grid101;
+    for (int g = 0; g <= 100; ++g) grid101.x[g] = (double)g * 0.01;   // == np.linspace(0, 1, 101) bit for bit
+    grid101.x[100] = 1.0;
+    for (int g = 0; g < 100; ++g) grid101.d[g] = grid101.x[g + 1] - grid101.x[g];
+    const int64_t items = nt * ix->class_groups;
+    ap_kernel<<<(unsigned)ceil_div(items, kApThreads / 32), kApThreads, 0, stream>>>(ap, grid101);
+    ORIE_LAUNCH_CHECK();
+    finalize_kernel<<<(unsigned)ceil_div(nt, 128), 128, 0, stream>>>(ap.partial, nt, ix->class_groups, ix->T, N, reward, detail);
+    ORIE_LAUNCH_CHECK();
+    return ORIE_OK;
+}

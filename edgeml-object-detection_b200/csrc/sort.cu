@@ -1,0 +1,221 @@
+// Device primitives: stable LSD radix sort of (u64 key, u32 value) pairs and an
+// exclusive u32 scan.  Hand-written for sm_100a; used by the one-off dataset
+// index build (index.cu).  The sort is the engine's "sort by (class,
+// confidence)" — done ONCE per dataset instead of once per target as
+// lib/metrics.py:101 does (np.argsort(-conf) inside every ap_per_class call).
+#include "common.cuh"
+
+namespace orie {
+
+// ----------------------------------------------------------------------------
+// exclusive scan
+// ----------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 4096
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_tile_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int64_t n,
+                 uint32_t *__restrict__ tile_sums, uint32_t *__restrict__ total) {
+    __shared__ uint32_t warp_sums[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        int64_t k = base + i;
+        v[i] = k < n ? in[k] : 0u;
+        sum += v[i];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < kScanThreads / 32 ? warp_sums[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(kFull, wi, d);
+            if (lane >= d) wi += y;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = wi - w;  // exclusive
+        if (lane == kScanThreads / 32 - 1) {
+            if (tile_sums) tile_sums[blockIdx.x] = wi;
+            if (total && gridDim.x == 1) *total = wi;
+        }
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[warp] + (incl - sum);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        int64_t k = base + i;
+        if (k < n) out[k] = run;
+        run += v[i];
+    }
+}
+
+__global__ void scan_add_kernel(uint32_t *__restrict__ out, int64_t n, const uint32_t *__restrict__ tile_offs) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] += tile_offs[k / kScanTile];
+}
+
+size_t scan_scratch_bytes(int64_t n) {
+    size_t bytes = 256;
+    while (n > kScanTile) {
+        n = ceil_div(n, kScanTile);
+        bytes += round_up(n * 4, 256);
+    }
+    return bytes;
+}
+
+int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *total, void *scratch, cudaStream_t st) {
+    if (n <= 0) {
+        if (total) ORIE_CUDA(cudaMemsetAsync(total, 0, 4, st));
+        return ORIE_OK;
+    }
+    const int64_t tiles = ceil_div(n, kScanTile);
+    if (tiles == 1) {
+        scan_tile_kernel<<<1, kScanThreads, 0, st>>>(in, out, n, nullptr, total);
+        ORIE_LAUNCH_CHECK();
+        return ORIE_OK;
+    }
+    uint32_t *sums = (uint32_t *)scratch;
+    void *rest = (char *)scratch + round_up(tiles * 4, 256);
+    scan_tile_kernel<<<(unsigned)tiles, kScanThreads, 0, st>>>(in, out, n, sums, nullptr);
+    ORIE_LAUNCH_CHECK();
+    ORIE_TRY(exclusive_scan_u32(sums, sums, tiles, total, rest, st));
+    scan_add_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(out, n, sums);
+    ORIE_LAUNCH_CHECK();
+    return ORIE_OK;
+}
+
+// ----------------------------------------------------------------------------
+// radix sort (8-bit digits, stable)
+// ----------------------------------------------------------------------------
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortSteps = 8;                       // 32-item steps per warp
+constexpr int kSortTile = kSortThreads * kSortSteps;  // 2048 items per block
+
+__device__ __forceinline__ int digit_of(uint64_t key, int shift, uint32_t mask) {
+    return (int)((uint32_t)(key >> shift) & mask);
+}
+
+// hist[digit * nblocks + block] = number of items of this block with that digit
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint32_t mask,
+                  uint32_t *__restrict__ hist, int nblocks) {
+    __shared__ uint32_t h[kRadix];
+    for (int i = threadIdx.x; i < kRadix; i += kSortThreads) h[i] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+    for (int s = 0; s < kSortSteps; ++s) {
+        int64_t k = base + s * kSortThreads + threadIdx.x;
+        if (k < n) atomicAdd(&h[digit_of(keys[k], shift, mask)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kRadix; i += kSortThreads) hist[(int64_t)i * nblocks + blockIdx.x] = h[i];
+}
+
+// Stable scatter.  Warp w of a block owns items [w*256, (w+1)*256) of the tile,
+// walked in 8 steps of 32 consecutive items; __match_any_sync ranks equal digits
+// inside a step, per-warp digit counters carry the rank across steps and warps.
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                     uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
+                     int shift, uint32_t mask, const uint32_t *__restrict__ offs, int nblocks) {
+    __shared__ uint32_t cnt[kSortWarps][kRadix];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * (32 * kSortSteps);
+    uint64_t k[kSortSteps];
+    uint32_t v[kSortSteps];
+    int dg[kSortSteps];
+#pragma unroll
+    for (int s = 0; s < kSortSteps; ++s) {
+        int64_t i = wbase + s * 32 + lane;
+        bool ok = i < n;
+        k[s] = ok ? keys[i] : 0ull;
+        v[s] = ok ? vals[i] : 0u;
+        dg[s] = ok ? digit_of(k[s], shift, mask) : kRadix;
+        unsigned peers = __match_any_sync(kFull, dg[s]);
+        if (ok && lane == (__ffs(peers) - 1)) cnt[warp][dg[s]] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const int d = threadIdx.x;  // kSortThreads == kRadix
+        uint32_t run = offs[(int64_t)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            uint32_t c = cnt[w][d];
+            cnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < kSortSteps; ++s) {
+        bool ok = dg[s] < kRadix;
+        unsigned peers = __match_any_sync(kFull, dg[s]);
+        uint32_t pos = 0;
+        if (ok) pos = cnt[warp][dg[s]] + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+        if (ok) {
+            keys_out[pos] = k[s];
+            vals_out[pos] = v[s];
+            if (lane == (__ffs(peers) - 1)) cnt[warp][dg[s]] += __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+static_assert(kSortThreads == kRadix, "one thread per digit in the carry pass");
+
+size_t radix_scratch_bytes(int64_t n) {
+    int64_t nblocks = ceil_div(n > 0 ? n : 1, kSortTile);
+    int64_t h = nblocks * kRadix;
+    return round_up(h * 4, 256) + scan_scratch_bytes(h);
+}
+
+int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
+                     int bit_lo, int bit_hi, void *scratch, cudaStream_t st) {
+    if (n <= 1 || bit_hi <= bit_lo) return ORIE_OK;
+    if (n >= (int64_t)1 << 31) {
+        set_error("radix_sort_pairs: n=%lld exceeds 2^31-1", (long long)n);
+        return ORIE_ELIMIT;
+    }
+    const int nblocks = (int)ceil_div(n, kSortTile);
+    uint32_t *hist = (uint32_t *)scratch;
+    void *scan_scratch = (char *)scratch + round_up((int64_t)nblocks * kRadix * 4, 256);
+    uint64_t *kin = keys, *kout = keys_tmp;
+    uint32_t *vin = vals, *vout = vals_tmp;
+    for (int lo = bit_lo; lo < bit_hi; lo += kRadixBits) {
+        const int bits = (bit_hi - lo) < kRadixBits ? (bit_hi - lo) : kRadixBits;
+        const uint32_t mask = (1u << bits) - 1u;
+        radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, n, lo, mask, hist, nblocks);
+        ORIE_LAUNCH_CHECK();
+        ORIE_TRY(exclusive_scan_u32(hist, hist, (int64_t)nblocks * kRadix, nullptr, scan_scratch, st));
+        radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, lo, mask, hist, nblocks);
+        ORIE_LAUNCH_CHECK();
+        uint64_t *tk = kin; kin = kout; kout = tk;
+        uint32_t *tv = vin; vin = vout; vout = tv;
+    }
+    if (kin != keys) {
+        ORIE_CUDA(cudaMemcpyAsync(keys, kin, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+        ORIE_CUDA(cudaMemcpyAsync(vals, vin, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return ORIE_OK;
+}
+
+}  // namespace orie

@@ -1,0 +1,257 @@
+"""Host side of the engine: device residency, kernel sequencing, target waves
+and multi-GPU sharding.  PyTorch is used only for device memory, streams and
+``torch.distributed``; every computation is a kernel of liborie_b200.so called
+through the C ABI (``_lib``).
+
+Public surface (mirrors the reference's drivers, ``reward.py:16-93``):
+
+    eng = Engine(packed, iouv=[0.5])            # H2D + TP matching + index build
+    eng.dcsb()                                   # reward.py:55-69
+    eng.orie(num_ensemble, ens_matrix=...)       # reward.py:16-52 with explicit ensembles
+    eng.orie(num_ensemble, seed=...)             # same, device-side ensemble draw
+    compute_rewards(packed, method, ...)         # main()'s reward phase incl. NaN -> 0
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .data import Packed
+
+IOU_05 = np.array([0.5])
+IOU_05_095 = np.linspace(0.5, 0.95, 10)
+
+
+def clamp_ensemble(num_images: int, num_ensemble: int) -> int:
+    """reward.py:28-34."""
+    return max(0, min(int(num_ensemble), int(num_images) - 1))
+
+
+def shard_range(num_images: int, rank: int, world: int):
+    """Contiguous target block of ``rank``; boundaries are multiples of 32
+    (targets are processed one per warp lane)."""
+    batches = (num_images + 31) // 32
+    per = (batches + world - 1) // world
+    t0 = min(rank * per * 32, num_images)
+    t1 = min((rank + 1) * per * 32, num_images)
+    return t0, t1 - t0
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    def __init__(self, packed: Packed, iouv=IOU_05, device=None, seg_chunks: int = 0, stream=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("orie_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.iouv = np.ascontiguousarray(np.asarray(iouv, dtype=np.float64))
+        self.T = int(len(self.iouv))
+        self.M, self.Cn = int(packed.num_images), int(packed.num_classes)
+        self._handle = C.c_void_p(0)
+        self._ws = None
+        with torch.cuda.device(self.device):
+            self.stream = stream or torch.cuda.current_stream()
+            with torch.cuda.stream(self.stream):
+                self._upload(packed)
+                self._match()
+                self._build_index(seg_chunks)
+
+    # ------------------------------------------------------------------ setup
+    def _dev(self, a: np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if t.numel() == 0:
+            return torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        return t.pin_memory().to(self.device, non_blocking=True)
+
+    def _upload(self, p: Packed):
+        self.h2d_bytes = p.nbytes()
+        self.w_off, self.w_box, self.w_conf, self.w_cls = map(self._dev, (p.w_off, p.w_box, p.w_conf, p.w_cls))
+        self.s_off, self.s_box, self.s_conf, self.s_cls = map(self._dev, (p.s_off, p.s_box, p.s_conf, p.s_cls))
+        self.l_off, self.l_box, self.l_cls = map(self._dev, (p.l_off, p.l_box, p.l_cls))
+        self.Dw, self.Ds, self.G = len(p.w_cls), len(p.s_cls), len(p.l_cls)
+
+    def _s(self):
+        return C.c_void_p(self.stream.cuda_stream)
+
+    def _match(self):
+        dev = self.device
+        iou_p = self.iouv.ctypes.data_as(C.POINTER(C.c_double))
+
+        def run(box, cls, off, n):
+            tp = torch.zeros(max(n, 1), dtype=torch.int16, device=dev)
+            mi = torch.full((max(n, 1),), -1, dtype=torch.int32, device=dev)
+            bi = torch.zeros(max(n, 1), dtype=torch.float64, device=dev)
+            _lib.check(self.lib.orie_match(_ptr(box), _ptr(cls), _ptr(off), _ptr(self.l_box), _ptr(self.l_cls),
+                                           _ptr(self.l_off), iou_p, self.T, self.M, _ptr(tp), _ptr(mi), _ptr(bi), self._s()))
+            return tp, mi, bi
+
+        self.w_tp, self.w_match, self.w_biou = run(self.w_box, self.w_cls, self.w_off, self.Dw)
+        self.s_tp, self.s_match, self.s_biou = run(self.s_box, self.s_cls, self.s_off, self.Ds)
+
+    def _build_index(self, seg_chunks):
+        h = C.c_void_p(0)
+        _lib.check(self.lib.orie_index_build(
+            self.M, self.Cn, self.T, _ptr(self.w_off), _ptr(self.w_cls), _ptr(self.w_conf), _ptr(self.w_tp),
+            _ptr(self.s_off), _ptr(self.s_cls), _ptr(self.s_conf), _ptr(self.s_tp), _ptr(self.l_off), _ptr(self.l_cls),
+            int(seg_chunks), self._s(), C.byref(h)))
+        self._handle = h
+        info = _lib.IndexInfo()
+        _lib.check(self.lib.orie_index_info(h, C.byref(info)))
+        self.info = {k: int(getattr(info, k)) for k, _ in info._fields_}
+
+    def close(self):
+        if self._handle:
+            self.lib.orie_index_destroy(self._handle)
+            self._handle = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---------------------------------------------------------------- results
+    def tp_flags(self):
+        """(weak bool[Dw,T], strong bool[Ds,T], weak match int32[Dw], strong match int32[Ds]) on the host."""
+        self.stream.synchronize()
+        bits = np.arange(self.T)
+
+        def expand(tp, n):
+            m = tp[:n].cpu().numpy().view(np.uint16).astype(np.int64)
+            return ((m[:, None] >> bits[None, :]) & 1).astype(bool)
+
+        return (expand(self.w_tp, self.Dw), expand(self.s_tp, self.Ds),
+                self.w_match[:self.Dw].cpu().numpy(), self.s_match[:self.Ds].cpu().numpy())
+
+    def dcsb(self) -> np.ndarray:
+        out = torch.empty(self.M, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            _lib.check(self.lib.orie_dcsb(_ptr(self.w_conf), _ptr(self.w_off), _ptr(self.s_conf), _ptr(self.s_off),
+                                          self.M, _ptr(out), self._s()))
+        return out.cpu().numpy()
+
+    def workspace_bytes(self, nt: int) -> int:
+        return int(self.lib.orie_reward_workspace_bytes(self._handle, int(nt)))
+
+    def wave_size(self, nt: int, budget_bytes: int) -> int:
+        """Largest multiple of 32 targets whose workspace fits the budget."""
+        if self.workspace_bytes(nt) <= budget_bytes:
+            return nt
+        lo, hi = 1, (nt + 31) // 32
+        while lo < hi:
+            mid = (lo + hi + 1) // 2
+            if self.workspace_bytes(mid * 32) <= budget_bytes:
+                lo = mid
+            else:
+                hi = mid - 1
+        return lo * 32
+
+    def _workspace(self, nbytes: int):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def orie_device(self, num_ensemble: int, ens_matrix=None, seed: int = 0, t0: int = 0, nt: int | None = None,
+                    workspace_budget: int = 8 << 30, detail: bool = False):
+        """Rewards of targets [t0, t0+nt) as a device tensor (asynchronous on the
+        engine's stream).  ``ens_matrix``: int32[nt, N] explicit ensembles (host or
+        device); otherwise ensembles are drawn on the device from ``seed``."""
+        nt = self.M - t0 if nt is None else int(nt)
+        N = clamp_ensemble(self.M, num_ensemble)
+        dev = self.device
+        words = self.info["ens_words"]
+        reward = torch.empty(max(nt, 1), dtype=torch.float64, device=dev)
+        det = torch.empty((max(nt, 1), 3), dtype=torch.float64, device=dev) if detail else None
+        if nt == 0:
+            return (reward[:0], det[:0]) if detail else reward[:0]
+        with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            if ens_matrix is not None:
+                em = ens_matrix if torch.is_tensor(ens_matrix) else torch.from_numpy(
+                    np.ascontiguousarray(ens_matrix, dtype=np.int32))
+                if em.shape != (nt, N):
+                    raise ValueError(f"ens_matrix must be int32[{nt}, {N}], got {tuple(em.shape)}")
+                if em.device != dev:
+                    em = (em.pin_memory() if em.numel() else em).to(dev, non_blocking=True)
+                em = em.to(torch.int32).contiguous()
+            wave = self.wave_size(nt, workspace_budget)
+            ws = self._workspace(self.workspace_bytes(wave))
+            bits = torch.empty((wave, words), dtype=torch.int32, device=dev)
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+            for a in range(0, nt, wave):
+                n = min(wave, nt - a)
+                if ens_matrix is not None:
+                    _lib.check(self.lib.orie_ensemble_from_indices(self._handle, t0 + a, n, _ptr(em[a:a + n]), N,
+                                                                   _ptr(bits), _ptr(status), self._s()))
+                else:
+                    _lib.check(self.lib.orie_ensemble_sample(self._handle, t0 + a, n, N, int(seed) & (2**64 - 1),
+                                                             _ptr(bits), self._s()))
+                _lib.check(self.lib.orie_reward(self._handle, t0 + a, n, _ptr(bits), N, _ptr(ws), ws.numel(),
+                                                _ptr(reward[a:]), _ptr(det[a:]) if detail else C.c_void_p(0), self._s()))
+            self._status = status
+        return (reward[:nt], det[:nt]) if detail else reward[:nt]
+
+    def sample_bits(self, num_ensemble: int, seed: int = 0, t0: int = 0, nt=None) -> np.ndarray:
+        """uint32[nt, ens_words] bitmaps the device-side draw produces for (seed, target)."""
+        nt = self.M - t0 if nt is None else int(nt)
+        N = clamp_ensemble(self.M, num_ensemble)
+        bits = torch.empty((max(nt, 1), self.info["ens_words"]), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            _lib.check(self.lib.orie_ensemble_sample(self._handle, t0, nt, N, int(seed) & (2**64 - 1), _ptr(bits), self._s()))
+        return bits[:nt].cpu().numpy().view(np.uint32)
+
+    def check_status(self):
+        st = int(self._status.item()) if getattr(self, "_status", None) is not None else 0
+        if st:
+            raise _lib.OrieError(5, "ensemble index out of range, equal to its target, or repeated"
+                                    f" (status {st})")
+
+    def orie(self, num_ensemble: int, ens_matrix=None, seed: int = 0, t0: int = 0, nt=None, **kw) -> np.ndarray:
+        out = self.orie_device(num_ensemble, ens_matrix, seed, t0, nt, **kw)
+        if isinstance(out, tuple):
+            r = tuple(x.cpu().numpy() for x in out)
+        else:
+            r = out.cpu().numpy()
+        self.check_status()
+        return r
+
+
+def compute_rewards(packed: Packed, method: str = "orie", num_ensemble: int = 1000, iouv=IOU_05, ens_matrix=None,
+                    seed: int = 0, device=None, distributed: bool = False):
+    """Reward vector of the whole dataset (what ``reward.py:main`` computes
+    between its two timers, plus ``set_data``'s matching).  With
+    ``distributed=True`` (under torchrun, NCCL) every rank computes its target
+    shard and the slices are combined with one all-gather."""
+    method = method.lower()
+    if method == "ori":
+        method, num_ensemble = "orie", 0
+    eng = Engine(packed, iouv=iouv, device=device)
+    try:
+        if method == "dcsb":
+            return eng.dcsb()
+        if method != "orie":
+            raise ValueError(f"unknown method {method!r}")
+        M = eng.M
+        if not distributed:
+            return eng.orie(num_ensemble, ens_matrix=ens_matrix, seed=seed)
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        t0, nt = shard_range(M, rank, world)
+        sub = None if ens_matrix is None else ens_matrix[t0:t0 + nt]
+        mine = eng.orie_device(num_ensemble, ens_matrix=sub, seed=seed, t0=t0, nt=nt)
+        per = shard_range(M, 0, world)[1]
+        pad = torch.zeros(per, dtype=torch.float64, device=eng.device)
+        pad[:nt] = mine
+        gathered = torch.empty(per * world, dtype=torch.float64, device=eng.device)
+        eng.stream.synchronize()
+        dist.all_gather_into_tensor(gathered, pad)
+        eng.check_status()
+        return gathered[:M].cpu().numpy()
+    finally:
+        eng.close()

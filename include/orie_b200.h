@@ -1,0 +1,147 @@
+/*
+ * orie_b200.h — C ABI of the B200-native ORIE / ORI / DCSB reward engine.
+ *
+ * The reference (qiujiaming315/edgeml-object-detection) is pure Python and has
+ * no FFI of its own; the boundary it offers is the reward.py CLI, the on-disk
+ * formats and three Python call signatures.  Every entry point
+ * below names the reference code it replaces (paths relative to the upstream
+ * repository root).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add to bind them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array pointer is a DEVICE pointer
+ *     unless its name ends in _host;
+ *   - the caller owns all buffers; the only allocations made inside are the
+ *     ones owned by an orie_index_t (created by orie_index_build, released by
+ *     orie_index_destroy).  Scratch for the reward pass is a caller-provided
+ *     workspace (orie_reward_workspace_bytes);
+ *   - work is enqueued on the given CUDA stream and is asynchronous, except
+ *     orie_index_build and the *_host helpers, which synchronise that stream;
+ *   - return value 0 = ORIE_OK, otherwise an ORIE_E* code; orie_last_error()
+ *     returns a thread-local message for the last failure on this thread;
+ *   - no global mutable state: one host thread per GPU may drive its own
+ *     index/workspace concurrently with others.
+ *
+ * Data layout ("packed dataset")
+ *   M images, C dense class ids [0,C), T IoU thresholds (1..16).
+ *   Detections of one detector: CSR by image — off int64[M+1], box f64[D,4]
+ *   (x1,y1,x2,y2 = lib/metrics.py:6-18 applied on the host), conf f64[D],
+ *   cls int32[D]; row order inside an image = file order.  Labels likewise
+ *   without conf.
+ */
+#ifndef ORIE_B200_H
+#define ORIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *orie_stream_t; /* == cudaStream_t */
+
+enum {
+    ORIE_OK = 0,
+    ORIE_EINVAL = 1,     /* bad argument */
+    ORIE_ECUDA = 2,      /* CUDA runtime error (message has the detail) */
+    ORIE_ELIMIT = 3,     /* input exceeds a documented engine limit */
+    ORIE_EWORKSPACE = 4, /* workspace too small */
+    ORIE_EDATA = 5       /* inconsistent data (e.g. ensemble index out of range) */
+};
+
+#define ORIE_MAX_THRESHOLDS 16
+#define ORIE_MAX_LABELS_PER_IMAGE 4096
+
+const char *orie_last_error(void);
+int orie_version(void);
+
+/*
+ * TP matching of every detection of every image at T IoU thresholds.
+ * Replaces lib/metrics.py:38-64 (box_correct) + :67-86 (box_iou) as driven per
+ * image by lib/data.py:63-83 (set_data).  FP64, upstream's operation order, no
+ * FMA contraction.  iouv_host: host array of T thresholds (pass numpy's
+ * np.linspace(0.5,0.95,10) or [0.5] verbatim).
+ *   tp_mask[d]   bit t set  <=> upstream's correct[d, t]
+ *   match_idx[d] label row (within the image) the detection is matched to at
+ *                every threshold where it is a TP; -1 if it is a TP nowhere
+ *   best_iou[d]  IoU with its best same-class label (0 if none); may be NULL
+ */
+int orie_match(const double *det_box, const int32_t *det_cls, const int64_t *det_off,
+               const double *lab_box, const int32_t *lab_cls, const int64_t *lab_off,
+               const double *iouv_host, int T, int64_t M,
+               uint16_t *tp_mask, int32_t *match_idx, double *best_iou, orie_stream_t stream);
+
+/*
+ * DCSB reward of every image: #(strong conf > 0.5) - #(weak conf > 0.5).
+ * Replaces reward.py:55-69 (compute_dcsb).  out: int64[M].
+ */
+int orie_dcsb(const double *w_conf, const int64_t *w_off, const double *s_conf, const int64_t *s_off,
+              int64_t M, int64_t *out, orie_stream_t stream);
+
+/*
+ * Dataset index: the weak detections sorted once by (class, confidence desc)
+ * (device radix sort), laid out in padded 32-slot chunks / segments, the
+ * true-positive event table, the strong detections' insertion ranks, the
+ * per-image own-detection lists and the class-sorted label stream.  It is the
+ * target-independent part of what reward.py:40-49 + lib/metrics.py:100-104
+ * recompute for every target (gather + argsort + unique).
+ */
+typedef struct orie_index orie_index_t;
+
+typedef struct {
+    int64_t num_images, num_classes;
+    int32_t num_thresholds, seg_chunks;
+    int64_t num_weak, num_strong, num_labels;
+    int64_t slots, segments, events;          /* detection stream */
+    int64_t label_slots, label_segments;      /* label stream */
+    int64_t class_groups;                     /* AP work items per target */
+    int64_t ens_words;                        /* uint32 words per ensemble bitmap */
+    int64_t device_bytes;                     /* bytes owned by the index */
+} orie_index_info_t;
+
+int orie_index_build(int64_t M, int64_t C, int T,
+                     const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
+                     const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
+                     const int64_t *l_off, const int32_t *l_cls,
+                     int seg_chunks /* 0 = auto */, orie_stream_t stream, orie_index_t **out);
+void orie_index_destroy(orie_index_t *idx);
+int orie_index_info(const orie_index_t *idx, orie_index_info_t *info);
+
+/*
+ * Ensembles.  An ensemble is a bitmap over images: uint32[ens_words] per
+ * target, bit e set <=> image e is in the target's ensemble.  Targets are the
+ * contiguous image range [t0, t0+nt).
+ *
+ * orie_ensemble_from_indices: explicit index lists ens_idx int32[nt, N]
+ *   (row r = ensemble of target t0+r; the arange/shift/permutation[:N] draw of
+ *   reward.py:35-38 regenerated on the host for parity runs).  status (device
+ *   int32[1], zero-initialised by the caller) receives a non-zero value if an
+ *   index is out of range, equals its target, or repeats.
+ * orie_ensemble_sample: device-side draw of N distinct images != target per
+ *   target (counter-based generator keyed by (seed, target), so the result does
+ *   not depend on how targets are sharded over GPUs).  Replaces reward.py:35-38
+ *   for throughput runs.
+ */
+int orie_ensemble_from_indices(const orie_index_t *idx, int64_t t0, int64_t nt, const int32_t *ens_idx, int64_t N,
+                               uint32_t *ens_bits, int32_t *status, orie_stream_t stream);
+int orie_ensemble_sample(const orie_index_t *idx, int64_t t0, int64_t nt, int64_t N, uint64_t seed,
+                         uint32_t *ens_bits, orie_stream_t stream);
+
+/*
+ * ORIE rewards of targets [t0, t0+nt):
+ *   reward[r] = (N+1) * ( mAP(E_weak + strong_t) - mAP(E_weak + weak_t) ), NaN -> 0.
+ * Replaces reward.py:16-52 (compute_orie) + :86 (NaN -> 0) and, inside it,
+ * lib/metrics.py:89-124 (ap_per_class) + :127-148 (compute_ap).  N is the
+ * (already clamped) ensemble size used for the (N+1) multiplier; N = 0 is ORI.
+ * detail (nullable): f64[nt,3] = (sum of weak APs, sum of strong APs, number
+ * of ground-truth classes) per target, for parity checks.
+ */
+size_t orie_reward_workspace_bytes(const orie_index_t *idx, int64_t nt);
+int orie_reward(const orie_index_t *idx, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
+                void *workspace, size_t workspace_bytes, double *reward, double *detail, orie_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORIE_B200_H */

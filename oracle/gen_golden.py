@@ -1,0 +1,68 @@
+"""Freeze golden vectors from the LIVE reference (run in the build container).
+
+    python oracle/gen_golden.py
+
+Writes tests/golden/*.npz.  Each fixture holds a small synthetic dataset in
+file-content form plus what the unmodified upstream code computed for it:
+``box_correct`` TP flags (through ``set_data`` for T=1 and through the
+T-generic glue for T=10), ``compute_orie`` with ``np.random.seed(base+idx)``
+before every sequential call, and ``compute_dcsb``.  The datasets are written
+to a temporary directory in the reference's on-disk formats and read back by
+the reference's own loader, so the loader is part of what is pinned.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import orie_b200  # noqa: E402,F401
+from orie_b200 import synth  # noqa: E402
+from oracle import ref_harness as R  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = [
+    # name, config, M, seed, generator kwargs, [(T, N, base_seed)]
+    ("coco48", "smoke500", 48, 31, dict(empty_det_frac=0.05), [(1, 12, 500), (10, 12, 500), (10, 0, 7), (1, 1000, 9)]),
+    ("voc40", "voc4952", 40, 32, dict(empty_det_frac=0.0, zipf=1.0), [(10, 20, 11), (1, 39, 12)]),
+]
+
+
+def flat(cache, T):
+    tp = [c[0].reshape(-1, T) for c in cache]
+    return np.concatenate(tp, axis=0) if tp else np.zeros((0, T), dtype=bool)
+
+
+def main():
+    assert R.available(), "needs /root/reference"
+    os.makedirs(OUT, exist_ok=True)
+    for name, config, M, seed, kw, runs in CASES:
+        ds = synth.make(config, num_images=M, seed=seed, **kw)
+        # make the edge cases explicit: an image without labels but with detections, one with nothing at all
+        out = dict(names=np.array(ds.names), num_classes=ds.num_classes,
+                   l_off=ds.labels.off, l_rows=ds.labels.rows, w_off=ds.weak.off, w_rows=ds.weak.rows,
+                   s_off=ds.strong.off, s_rows=ds.strong.rows)
+        with tempfile.TemporaryDirectory() as d:
+            w, s, l = synth.write_dirs(ds, d)
+            caches = {}
+            for T in sorted({r[0] for r in runs}):
+                iouv = None if T == 1 else np.linspace(0.5, 0.95, 10)
+                caches[T] = R.ref_set_data(w, s, l, iouv)
+                wd, sd, lab = caches[T]
+                out[f"w_tp_T{T}"] = flat(wd, T)
+                out[f"s_tp_T{T}"] = flat(sd, T)
+            out["dcsb"] = R.ref_dcsb(*caches[runs[0][0]][:2])
+            for T, N, base in runs:
+                wd, sd, lab = caches[T]
+                out[f"orie_T{T}_N{N}_seed{base}"] = R.ref_orie(wd, sd, lab, N, base)
+        out["runs"] = np.array(runs, dtype=np.int64)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

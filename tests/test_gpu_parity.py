@@ -1,0 +1,110 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from helpers import O, flat_tp, make_packed, oracle_cache
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(pk, iouv, **kw):
+    from orie_b200.engine import Engine
+    return Engine(pk, iouv=iouv, **kw)
+
+
+@pytest.mark.parametrize("T", [1, 10])
+def test_matching_bit_exact(T):
+    iouv = O.IOU_05 if T == 1 else O.IOU_05_095
+    _, pk = make_packed(M=300, seed=11, empty_det_frac=0.03)
+    eng = _engine(pk, iouv)
+    wtp, stp, wm, sm = eng.tp_flags()
+    wd, sd, _ = oracle_cache(pk, iouv)
+    assert np.array_equal(wtp, flat_tp(wd, len(pk.w_cls), T))
+    assert np.array_equal(stp, flat_tp(sd, len(pk.s_cls), T))
+    # match indices: the label a TP is matched to
+    for off, box, cls, got, tp in ((pk.w_off, pk.w_box, pk.w_cls, wm, wtp), (pk.s_off, pk.s_box, pk.s_cls, sm, stp)):
+        for i in range(0, pk.num_images, 7):
+            a, b = off[i], off[i + 1]
+            la, lb = pk.l_off[i], pk.l_off[i + 1]
+            _, best, _ = O.match_detections(box[a:b], cls[a:b], pk.l_box[la:lb], pk.l_cls[la:lb], iouv)
+            want = np.where(tp[a:b].any(axis=1), best, -1)
+            assert np.array_equal(got[a:b], want)
+    eng.close()
+
+
+def test_dcsb_exact():
+    _, pk = make_packed(M=300, seed=12, empty_det_frac=0.05)
+    eng = _engine(pk, O.IOU_05)
+    wd, sd, _ = oracle_cache(pk, O.IOU_05)
+    assert np.array_equal(eng.dcsb(), O.dcsb_all(wd, sd))
+    eng.close()
+
+
+@pytest.mark.parametrize("M,N,T,segch", [(200, 50, 10, 0), (200, 50, 1, 2), (96, 0, 10, 1), (70, 69, 10, 0), (257, 31, 1, 3)])
+def test_orie_explicit_ensembles(M, N, T, segch):
+    iouv = O.IOU_05 if T == 1 else O.IOU_05_095
+    _, pk = make_packed(M=M, seed=100 + M, empty_det_frac=0.04)
+    eng = _engine(pk, iouv, seg_chunks=segch)
+    em = O.ensemble_matrix(M, N, 77)
+    got, det = eng.orie(N, ens_matrix=em, detail=True)
+    wd, sd, lc = oracle_cache(pk, iouv)
+    want = O.orie_all(wd, sd, lc, em)
+    err = np.abs(got - want)
+    assert err.max() < 1e-9, (err.max(), int(err.argmax()), got[err.argmax()], want[err.argmax()])
+    # per-target AP sums (detail) for a few targets
+    for i in range(0, M, 37):
+        _, wap, sap = O.orie_one(i, wd, sd, lc, em[i])
+        assert abs(det[i, 0] - wap.sum()) < 1e-9 and abs(det[i, 1] - sap.sum()) < 1e-9
+        assert det[i, 2] == wap.shape[0]
+    eng.close()
+
+
+def test_orie_waves_and_ranges_agree():
+    M, N = 200, 40
+    _, pk = make_packed(M=M, seed=5)
+    eng = _engine(pk, O.IOU_05_095)
+    em = O.ensemble_matrix(M, N, 3)
+    full = eng.orie(N, ens_matrix=em)
+    small = eng.orie(N, ens_matrix=em, workspace_budget=eng.workspace_bytes(64))
+    assert np.array_equal(full, small)
+    part = eng.orie(N, ens_matrix=em[64:160], t0=64, nt=96)
+    assert np.array_equal(full[64:160], part)
+    eng.close()
+
+
+def test_orie_sampled_ensembles():
+    import torch
+    M, N = 150, 60
+    _, pk = make_packed(M=M, seed=9)
+    eng = _engine(pk, O.IOU_05_095)
+    bits = eng.sample_bits(N, seed=1234)
+    assert bits.shape[0] == M
+    member = ((bits[:, :, None] >> np.arange(32)[None, None, :]) & 1).reshape(M, -1)[:, :M].astype(bool)
+    assert (member.sum(axis=1) == N).all()
+    assert not member[np.arange(M), np.arange(M)].any()
+    got = eng.orie(N, seed=1234)
+    wd, sd, lc = oracle_cache(pk, O.IOU_05_095)
+    em = np.stack([np.nonzero(member[i])[0] for i in range(M)])
+    want = O.orie_all(wd, sd, lc, em)
+    assert np.abs(got - want).max() < 1e-9
+    # more than half of the dataset -> complement path
+    N2 = 120
+    bits = eng.sample_bits(N2, seed=5)
+    member = ((bits[:, :, None] >> np.arange(32)[None, None, :]) & 1).reshape(M, -1)[:, :M].astype(bool)
+    assert (member.sum(axis=1) == N2).all() and not member[np.arange(M), np.arange(M)].any()
+    # different seeds differ, same seed repeats
+    assert np.array_equal(eng.sample_bits(N, seed=1234), eng.sample_bits(N, seed=1234))
+    assert not np.array_equal(eng.sample_bits(N, seed=1), eng.sample_bits(N, seed=2))
+    eng.close()
+
+
+def test_bad_ensemble_is_reported():
+    from orie_b200._lib import OrieError
+    M, N = 64, 5
+    _, pk = make_packed(M=M, seed=2)
+    eng = _engine(pk, O.IOU_05)
+    em = O.ensemble_matrix(M, N, 1)
+    em[3, 0] = 3      # a target inside its own ensemble
+    with pytest.raises(OrieError):
+        eng.orie(N, ens_matrix=em)
+    eng.close()
