@@ -23,7 +23,14 @@ void set_error(const char *fmt, ...);
         }                                                                                      \
     } while (0)
 
-#define ORIE_LAUNCH_CHECK() ORIE_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by this (n = launches since the last check)
+void count_launches(int n);
+#define ORIE_LAUNCH_CHECK_N(n) \
+    do {                       \
+        ::orie::count_launches(n); \
+        ORIE_CUDA(cudaGetLastError()); \
+    } while (0)
+#define ORIE_LAUNCH_CHECK() ORIE_LAUNCH_CHECK_N(1)
 
 #define ORIE_TRY(expr)                \
     do {                              \

@@ -53,13 +53,30 @@ __global__ void gather_keys_kernel(const uint32_t *__restrict__ src, const uint3
     keys[k] = (uint64_t)(src[vals[k]] >> shift);
 }
 
+// class histogram: per-block shared-memory bins (C <= kHistSmemBins), flushed with one global atomic per
+// non-empty bin; plain global atomics beyond that
+constexpr int kHistSmemBins = 8192;
+constexpr int kHistItemsPerBlock = 8192;
 __global__ void class_hist_kernel(const int32_t *__restrict__ cls, int64_t n, int64_t C, uint32_t *__restrict__ hist,
                                   int32_t *__restrict__ status) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    int c = cls[k];
-    if (c < 0 || c >= C) { atomicOr(status, 2); return; }
-    atomicAdd(&hist[c], 1u);
+    extern __shared__ uint32_t bins[];
+    const bool local = C <= kHistSmemBins;
+    if (local) {
+        for (int i = threadIdx.x; i < C; i += blockDim.x) bins[i] = 0;
+        __syncthreads();
+    }
+    const int64_t base = (int64_t)blockIdx.x * kHistItemsPerBlock;
+    const int64_t end = base + kHistItemsPerBlock < n ? base + kHistItemsPerBlock : n;
+    for (int64_t k = base + threadIdx.x; k < end; k += blockDim.x) {
+        const int c = cls[k];
+        if (c < 0 || c >= C) { atomicOr(status, 2); continue; }
+        atomicAdd(local ? &bins[c] : &hist[c], 1u);
+    }
+    if (local) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x)
+            if (bins[i]) atomicAdd(&hist[i], bins[i]);
+    }
 }
 
 __global__ void fill_u32_kernel(uint32_t *__restrict__ p, int64_t n, uint32_t v) {
@@ -215,17 +232,19 @@ static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
     return b;
 }
 
+// Allocations are stream-ordered (cudaMallocAsync on the device's default pool, whose release
+// threshold is raised once so that rebuilding an index does not go back to the OS every time).
 struct Builder {
     orie_index *ix;
     cudaStream_t st;
     std::vector<void *> temps;
     ~Builder() {
-        for (void *p : temps) cudaFree(p);
+        for (void *p : temps) cudaFreeAsync(p, st);
     }
     template <typename Tp>
     int temp(Tp **p, int64_t count) {
         void *q = nullptr;
-        ORIE_CUDA(cudaMalloc(&q, (size_t)std::max<int64_t>(count, 1) * sizeof(Tp)));
+        ORIE_CUDA(cudaMallocAsync(&q, (size_t)std::max<int64_t>(count, 1) * sizeof(Tp), st));
         temps.push_back(q);
         *p = (Tp *)q;
         return ORIE_OK;
@@ -234,9 +253,9 @@ struct Builder {
     int keep(Tp **p, int64_t count) {
         void *q = nullptr;
         size_t bytes = (size_t)std::max<int64_t>(count, 1) * sizeof(Tp);
-        ORIE_CUDA(cudaMalloc(&q, bytes));
+        ORIE_CUDA(cudaMallocAsync(&q, bytes, st));
         if (ix->n_allocs >= (int)(sizeof(ix->allocs) / sizeof(ix->allocs[0]))) {
-            cudaFree(q);
+            cudaFreeAsync(q, st);
             set_error("orie_index_build: allocation table full");
             return ORIE_EINVAL;
         }
@@ -296,6 +315,14 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
                  const int64_t *l_off, const int32_t *l_cls, int seg_chunks_req, cudaStream_t st) {
     Builder B{ix, st};
     const int64_t M = ix->M, C = ix->C;
+    {
+        int dev = 0;
+        cudaMemPool_t pool;
+        uint64_t keep_all = UINT64_MAX;
+        ORIE_CUDA(cudaGetDevice(&dev));
+        ORIE_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        ORIE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
+    }
     // ---- sizes (three small D2H reads)
     int64_t tails[3];
     ORIE_CUDA(cudaMemcpyAsync(&tails[0], w_off + M, 8, cudaMemcpyDeviceToHost, st));
@@ -348,13 +375,31 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     const int cbits = bits_for(C), ibits = bits_for(M), bbits = bits_for(ix->nbatch);
 
     // ---- image of every row; class histograms
-    if (Dw) image_of_row_kernel<<<grid_for(Dw), 256, 0, st>>>(w_off, M, Dw, img_w, status);
-    if (Ds) image_of_row_kernel<<<grid_for(Ds), 256, 0, st>>>(s_off, M, Ds, img_s, status);
-    if (G) image_of_row_kernel<<<grid_for(G), 256, 0, st>>>(l_off, M, G, img_l, status);
-    if (Dw) class_hist_kernel<<<grid_for(Dw), 256, 0, st>>>(w_cls, Dw, C, hist, status);
-    if (G) class_hist_kernel<<<grid_for(G), 256, 0, st>>>(l_cls, G, C, hist + C, status);
-    if (Ds) class_hist_kernel<<<grid_for(Ds), 256, 0, st>>>(s_cls, Ds, C, hist + 2 * C, status);  // range check
-    ORIE_LAUNCH_CHECK();
+    const size_t hist_smem = C <= kHistSmemBins ? (size_t)C * 4 : 0;
+    if (Dw) {
+        image_of_row_kernel<<<grid_for(Dw), 256, 0, st>>>(w_off, M, Dw, img_w, status);
+        ORIE_LAUNCH_CHECK();
+    }
+    if (Ds) {
+        image_of_row_kernel<<<grid_for(Ds), 256, 0, st>>>(s_off, M, Ds, img_s, status);
+        ORIE_LAUNCH_CHECK();
+    }
+    if (G) {
+        image_of_row_kernel<<<grid_for(G), 256, 0, st>>>(l_off, M, G, img_l, status);
+        ORIE_LAUNCH_CHECK();
+    }
+    if (Dw) {
+        class_hist_kernel<<<grid_for(Dw, kHistItemsPerBlock), 256, hist_smem, st>>>(w_cls, Dw, C, hist, status);
+        ORIE_LAUNCH_CHECK();
+    }
+    if (G) {
+        class_hist_kernel<<<grid_for(G, kHistItemsPerBlock), 256, hist_smem, st>>>(l_cls, G, C, hist + C, status);
+        ORIE_LAUNCH_CHECK();
+    }
+    if (Ds) {
+        class_hist_kernel<<<grid_for(Ds, kHistItemsPerBlock), 256, hist_smem, st>>>(s_cls, Ds, C, hist + 2 * C, status);  // range check
+        ORIE_LAUNCH_CHECK();
+    }
 
     // ---- global weak order: confidence desc (64-bit key), then class (stable)
     if (Dw) {
@@ -383,7 +428,12 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     }
     int64_t raw_chunks = 0;
     for (int64_t c = 0; c < C; ++c) raw_chunks += ceil_div((int64_t)h_hist[c] + 1, kChunk);
-    int seg_chunks = seg_chunks_req > 0 ? seg_chunks_req : (int)std::max<int64_t>(16, ceil_div(raw_chunks, 4096));
+    // Segment length: about two segments per average class (measured best for both the walk's load balance
+    // and the AP sweep on COCO-shaped data, profiles/), enough (batch, segment) warp items for >= 4 waves of
+    // 148 SMs x 8 warps, and no segment so long that a single warp becomes the tail of the walk.
+    const int64_t seg_target = std::max<int64_t>(2 * C, ceil_div(4 * 148 * 8, ix->nbatch));
+    int seg_chunks = seg_chunks_req > 0 ? seg_chunks_req
+                                        : (int)std::min<int64_t>(512, std::max<int64_t>(16, ceil_div(raw_chunks, seg_target)));
     ix->seg_chunks = seg_chunks;
     StreamLayout LD = make_layout(h_hist.data(), C, 1, seg_chunks);
     StreamLayout LL = make_layout(h_hist.data() + C, C, 0, seg_chunks);
@@ -415,11 +465,13 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     ORIE_TRY(B.keep(&ix->evbase, ix->nchunks));
     ORIE_TRY(B.keep(&ix->seg_ev0, ix->S));
     fill_u32_kernel<<<grid_for(ix->P), 256, 0, st>>>(ix->slot_img, ix->P, (uint32_t)M);
+    ORIE_LAUNCH_CHECK();
     ORIE_CUDA(cudaMemsetAsync(slot_tp, 0, (size_t)ix->P * 2, st));
-    if (Dw)
+    if (Dw) {
         place_slots_kernel<<<grid_for(Dw), 256, 0, st>>>(order_w, w_cls, img_w, w_tp, w_conf, Dw, d_cls_off, d_pad_off,
                                                        ix->slot_img, slot_tp, prank, conf_sorted);
-    ORIE_LAUNCH_CHECK();
+        ORIE_LAUNCH_CHECK();
+    }
 
     // ---- events
     uint32_t *d_total;
@@ -437,12 +489,14 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     ix->Ev = h_total;
     ORIE_TRY(B.keep(&ix->evmask, ix->Ev));
     event_mask_kernel<<<grid_for(ix->nchunks * 32), 256, 0, st>>>(slot_tp, ix->nchunks, ix->evbits, ix->evbase, ix->evmask);
+    ORIE_LAUNCH_CHECK();
     gather_seg_ev0_kernel<<<grid_for(ix->S), 256, 0, st>>>(ix->seg_chunk0, ix->S, ix->evbase, ix->seg_ev0);
     ORIE_LAUNCH_CHECK();
 
     // ---- strong: insertion slots, global (class, conf desc) order
     if (Ds) {
         strong_query_kernel<<<grid_for(Ds), 256, 0, st>>>(s_cls, s_conf, Ds, conf_sorted, d_cls_off, d_pad_off, q_s);
+        ORIE_LAUNCH_CHECK();
         conf_keys_kernel<<<grid_for(Ds), 256, 0, st>>>(s_conf, Ds, keys, vals);
         ORIE_LAUNCH_CHECK();
         ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, Ds, 0, 64, rscratch, st));
@@ -485,6 +539,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
             ORIE_LAUNCH_CHECK();
             ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, d.n, 0, ibits, rscratch, st));
             own_fill_kernel<<<grid_for(d.n), 256, 0, st>>>(vals, d.n, d.q, d.tp, d.own_q, d.own_m, ownpos);
+            ORIE_LAUNCH_CHECK();
             own_class_start_kernel<<<grid_for(d.n), 256, 0, st>>>(vals, d.n, d.cls, d.img, d.off, C, d.own_cs);
             ORIE_LAUNCH_CHECK();
             // batch-major: stable sort of the global order by image / 32
@@ -504,14 +559,17 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     ORIE_TRY(B.keep(&ix->lab_slot_img, ix->PL));
     ORIE_TRY(B.keep(&ix->gtcnt, M * C));
     ORIE_CUDA(cudaMemsetAsync(ix->gtcnt, 0, (size_t)(M * C) * 4, st));
-    if (ix->PL) fill_u32_kernel<<<grid_for(ix->PL), 256, 0, st>>>(ix->lab_slot_img, ix->PL, (uint32_t)M);
+    if (ix->PL) {
+        fill_u32_kernel<<<grid_for(ix->PL), 256, 0, st>>>(ix->lab_slot_img, ix->PL, (uint32_t)M);
+        ORIE_LAUNCH_CHECK();
+    }
     if (G) {
         label_keys_kernel<<<grid_for(G), 256, 0, st>>>(l_cls, img_l, G, C, keys, vals, ix->gtcnt);
         ORIE_LAUNCH_CHECK();
         ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, G, 0, cbits, rscratch, st));
         place_labels_kernel<<<grid_for(G), 256, 0, st>>>(keys, vals, G, d_lcls_off, d_lpad_off, ix->lab_slot_img);
+        ORIE_LAUNCH_CHECK();
     }
-    ORIE_LAUNCH_CHECK();
     ORIE_CUDA(cudaStreamSynchronize(st));
     return ORIE_OK;
 }
@@ -545,6 +603,7 @@ extern "C" int orie_index_build(int64_t M, int64_t C, int T,
     }
     orie_index *ix = new orie_index();
     ix->M = M; ix->C = C; ix->T = T;
+    ix->stream = stream;
     ix->nbatch = ceil_div(M, 32);
     ix->ens_words = ceil_div(M + 1, 32);
     ix->cls_per_warp = 32 / T;
@@ -560,7 +619,7 @@ extern "C" int orie_index_build(int64_t M, int64_t C, int T,
 
 extern "C" void orie_index_destroy(orie_index_t *ix) {
     if (!ix) return;
-    for (int i = 0; i < ix->n_allocs; ++i) cudaFree(ix->allocs[i]);
+    for (int i = 0; i < ix->n_allocs; ++i) cudaFreeAsync(ix->allocs[i], ix->stream);
     delete ix;
 }
 

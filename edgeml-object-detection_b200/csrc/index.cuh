@@ -46,6 +46,7 @@ struct orie_index {
     int64_t class_groups = 0;          // ceil(C / cls_per_warp)
 
     int64_t device_bytes = 0;
+    cudaStream_t stream = nullptr;   // stream the index was built on; its memory is freed on it
     void *allocs[48] = {};
     int n_allocs = 0;
 };

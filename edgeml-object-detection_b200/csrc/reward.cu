@@ -212,8 +212,9 @@ walk_kernel(const WalkParams p) {
 // K2: AP integration
 // ----------------------------------------------------------------------------
 struct Grid101 {
-    double x[101];   // np.linspace(0, 1, 101)
-    double d[100];   // np.diff(x)
+    double cw[102];   // cw[i]  = sum_{g<i} W_g,      W = trapezoid weight of grid point g of np.linspace(0,1,101)
+    double cwx[102];  // cwx[i] = sum_{g<i} W_g x_g
+    uint32_t ge[4];   // bit g: x[g] >= correctly rounded g/100 (decides exact rational ties, see ApVar)
 };
 
 struct ApParams {
@@ -232,54 +233,111 @@ struct ApParams {
     double *partial;    // [ntp][class_groups][3]
 };
 
-// Reverse-sweep state of one (class, threshold, variant) integral; see oracle/event_model.py:_Var.
+// Reverse-sweep state of one (class, threshold, variant) AP integral; oracle/event_model.py:_Var
+// is the CPU statement of the same thing and carries the argument for the three shortcuts:
+//  * below the last true positive np.interp's two knots carry the same envelope value, so the
+//    curve is y(x) = E = max_{k' > k} k'/p_{k'}; E is kept as an exact fraction (kE/pE) and only
+//    divided when a run of grid points actually samples it;
+//  * "x_g >= fl(k/n_l)" is decided in integers (100 k vs g n_l; exact ties by the constant ge table);
+//  * a run of grid points sharing one E contributes E * (cw[hi+1] - cw[lo]) to np.trapz; only the
+//    tail beyond the last true positive is a genuine linear ramp (lib/metrics.py:137-144), integrated
+//    in closed form with cw and cwx.
+// 1/p to ~1 ulp without the IEEE division sequence: float seed + two Newton steps.  Only used for
+// envelope values that are multiplied into the integral (tolerance 1e-9 on mAP), never for a comparison.
+__device__ __forceinline__ double fast_ratio(uint32_t num, uint32_t den) {
+    const double d = (double)den;
+    double r = (double)__frcp_rn((float)den);
+    r = __fma_rn(r, __fma_rn(-d, r, 1.0), r);
+    r = __fma_rn(r, __fma_rn(-d, r, 1.0), r);
+    return __dmul_rn((double)num, r);
+}
+
 struct ApVar {
-    double ap, y_next, E, r_cur, n_l;
-    int g, k;
+    double ap;
+    float inv_nl;
+    uint32_t kE, pE, k, n_l;
+    int g;                // highest grid point not yet integrated
     bool dead;
 
-    __device__ __forceinline__ void consume(const double *gx, const double *gd, double r_lo, double env_lo, double r_hi,
-                                            double env_hi) {
-        if (g >= 0 && gx[g] >= r_lo) {
-            const double slope = __ddiv_rn(__dsub_rn(env_hi, env_lo), __dsub_rn(r_hi, r_lo));
-            do {
-                const double x = gx[g];
-                const double y = (x == r_lo) ? env_lo : __dadd_rn(__dmul_rn(slope, __dsub_rn(x, r_lo)), env_lo);
-                ap = __dadd_rn(ap, __ddiv_rn(__dmul_rn(gd[g], __dadd_rn(y_next, y)), 2.0));
-                y_next = y;
-                --g;
-            } while (g >= 0 && gx[g] >= r_lo);
+    // smallest g with x_g >= (k100/100)/n_l in numpy's float comparison; k100 = 100 * (number of TPs)
+    __device__ __forceinline__ int grid_lo(const uint32_t *ge, uint64_t a) const {
+        int gl;
+        bool tie;
+        if (n_l < (1u << 25)) {                 // a <= 100 n_l < 2^32: 32-bit path
+            const uint32_t a32 = (uint32_t)a;
+            int q = (int)((float)a32 * inv_nl);                 // floor(a / n_l) within +-1
+            int r = (int)(a32 - (uint32_t)q * n_l);
+            if (r < 0) { --q; r += (int)n_l; }
+            else if (r >= (int)n_l) { ++q; r -= (int)n_l; }
+            gl = q + (r > 0);
+            tie = r == 0;
+        } else {
+            const uint64_t q = a / n_l;
+            const uint64_t r = a - q * n_l;
+            gl = (int)q + (r > 0);
+            tie = r == 0;
         }
+        if (tie && gl <= 100 && !((ge[gl >> 5] >> (gl & 31)) & 1u)) ++gl;
+        return gl;
     }
-    __device__ __forceinline__ void init(const double *gx, const double *gd, int K, int64_t n_p, uint32_t nl) {
-        ap = 0.0; y_next = 0.0; E = -1.0; g = 99; k = K; n_l = (double)nl; r_cur = 0.0;
+    __device__ __forceinline__ void init(const double *cw, const double *cwx, const uint32_t *ge, uint32_t K, uint32_t n_p,
+                                         uint32_t nl) {
+        ap = 0.0; g = 99; k = K; kE = 0; pE = 1; n_l = nl;
+        inv_nl = 1.0f / (float)nl;
         dead = (K == 0 || n_p == 0);
         if (dead) return;
-        const double r_k = __ddiv_rn((double)K, n_l);
-        consume(gx, gd, r_k, __ddiv_rn((double)K, (double)n_p), 1.0, 0.0);
-        r_cur = r_k;
+        const int gl = grid_lo(ge, (uint64_t)K * 100ull);
+        if (gl <= g) {
+            const double r_k = __ddiv_rn((double)K, (double)nl);
+            const double env = __ddiv_rn((double)K, (double)n_p);
+            const double slope = __ddiv_rn(__dsub_rn(0.0, env), __dsub_rn(1.0, r_k));
+            const double sw = __dsub_rn(cw[g + 1], cw[gl]);
+            const double swx = __dsub_rn(cwx[g + 1], cwx[gl]);
+            ap = __dadd_rn(__dmul_rn(slope, __dsub_rn(swx, __dmul_rn(r_k, sw))), __dmul_rn(env, sw));
+            g = gl - 1;
+        }
     }
     // the k-th true positive (k = current k) sits at 1-based rank pos
-    __device__ __forceinline__ void step(const double *gx, const double *gd, int64_t pos) {
+    __device__ __forceinline__ void step(const double *cw, const uint32_t *ge, uint32_t pos) {
         if (dead) return;
-        E = fmax(E, __ddiv_rn((double)k, (double)pos));
-        const double r_lo = __ddiv_rn((double)(k - 1), n_l);
-        const int64_t j = pos - 1;
-        const double prec_j = j == 0 ? 1.0 : __ddiv_rn((double)(k - 1), (double)j);
-        consume(gx, gd, r_lo, fmax(prec_j, E), r_cur, E);
-        r_cur = r_lo;
+        if ((uint64_t)k * pE > (uint64_t)kE * pos) { kE = k; pE = pos; }
+        const int gl = grid_lo(ge, (uint64_t)(k - 1) * 100ull);
+        if (gl <= g) {
+            ap = __dadd_rn(ap, __dmul_rn(fast_ratio(kE, pE), __dsub_rn(cw[g + 1], cw[gl])));
+            g = gl - 1;
+        }
         --k;
     }
 };
 
+// Cursor over the target's own detections of one class in one variant, walked from the back;
+// the current entry is cached in registers.
+struct OwnCursor {
+    const uint32_t *q, *cb;
+    const uint16_t *m;
+    int64_t ib, lo;
+    uint32_t cq, ccb;
+    bool ctp, valid;
+    __device__ __forceinline__ void load(int t) {
+        valid = ib >= lo;
+        if (valid) { cq = q[ib]; ccb = cb[ib]; ctp = (m[ib] >> t) & 1; }
+    }
+    __device__ __forceinline__ void init(const uint32_t *q_, const uint32_t *cb_, const uint16_t *m_, int64_t lo_, int64_t hi_, int t) {
+        q = q_; cb = cb_; m = m_; lo = lo_; ib = hi_ - 1; cq = 0; ccb = 0; ctp = false;
+        load(t);
+    }
+    __device__ __forceinline__ uint32_t before() const { return (uint32_t)(ib - lo + 1); }   // own entries still in front
+};
+
 constexpr int kApThreads = 128;
 
-__global__ void __launch_bounds__(kApThreads)
+__global__ void __launch_bounds__(kApThreads, 8)
 ap_kernel(const ApParams p, const Grid101 grid) {
-    __shared__ double gx[101];
-    __shared__ double gd[100];
-    for (int i = threadIdx.x; i < 101; i += kApThreads) gx[i] = grid.x[i];
-    for (int i = threadIdx.x; i < 100; i += kApThreads) gd[i] = grid.d[i];
+    __shared__ double cw[102];
+    __shared__ double cwx[102];
+    __shared__ uint32_t ge[4];
+    for (int i = threadIdx.x; i < 102; i += kApThreads) { cw[i] = grid.cw[i]; cwx[i] = grid.cwx[i]; }
+    if (threadIdx.x < 4) ge[threadIdx.x] = grid.ge[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t item = (int64_t)blockIdx.x * (kApThreads / 32) + (threadIdx.x >> 5);
@@ -298,59 +356,64 @@ ap_kernel(const ApParams p, const Grid101 grid) {
             if (t == 0) has_gt = 1.0;
             const int s0 = p.cls_seg0[c], s1 = p.cls_seg0[c + 1];
             const uint64_t *ev = p.ev + tl * p.Ev;
-            int64_t n_ens = 0;
-            int K_ens = 0;
+            uint32_t n_ens = 0, K_ens = 0;
             for (int s = s0; s < s1; ++s) {
                 n_ens += p.tot[(int64_t)s * p.ntp + tl];
                 const uint64_t *e = ev + p.seg_ev0[s];
                 const int ne = (int)p.evcnt[(int64_t)s * p.ntp + tl];
-                for (int i = 0; i < ne; ++i) K_ens += (int)((e[i] >> (32 + t)) & 1ull);
+                for (int i = 0; i < ne; ++i) K_ens += (uint32_t)((e[i] >> (32 + t)) & 1ull);
             }
             const int64_t wa = p.w_off[j] + p.own_w_cs[j * (p.C + 1) + c], wb = p.w_off[j] + p.own_w_cs[j * (p.C + 1) + c + 1];
             const int64_t sa = p.s_off[j] + p.own_s_cs[j * (p.C + 1) + c], sb = p.s_off[j] + p.own_s_cs[j * (p.C + 1) + c + 1];
-            int K_w = K_ens, K_s = K_ens;
+            uint32_t K_w = K_ens, K_s = K_ens;
             for (int64_t i = wa; i < wb; ++i) K_w += (p.own_w_m[i] >> t) & 1;
             for (int64_t i = sa; i < sb; ++i) K_s += (p.own_s_m[i] >> t) & 1;
             ApVar vw, vs;
-            vw.init(gx, gd, K_w, n_ens + (wb - wa), n_l);
-            vs.init(gx, gd, K_s, n_ens + (sb - sa), n_l);
+            vw.init(cw, cwx, ge, K_w, n_ens + (uint32_t)(wb - wa), n_l);
+            vs.init(cw, cwx, ge, K_s, n_ens + (uint32_t)(sb - sa), n_l);
+            // the target has no detection of this class from either detector: both variants are the same integral
+            const bool same = (wb == wa) && (sb == sa);
+            if (same) vs.dead = true;
             if (!(vw.dead && vs.dead)) {
-                int64_t ibw = wb - 1, ibs = sb - 1;
-                int64_t rem = n_ens;
+                OwnCursor ow, os;
+                ow.init(p.own_w_q, p.cb_w, p.own_w_m, wa, wb, t);
+                os.init(p.own_s_q, p.cb_s, p.own_s_m, sa, sb, t);
+                uint32_t rem = n_ens;
                 for (int s = s1 - 1; s >= s0; --s) {
                     rem -= p.tot[(int64_t)s * p.ntp + tl];
-                    const int64_t base = rem;
+                    const uint32_t base = rem;
                     const uint32_t slot0 = (uint32_t)p.seg_chunk0[s] * 32u;
                     const uint64_t *e = ev + p.seg_ev0[s];
                     const int ne = (int)p.evcnt[(int64_t)s * p.ntp + tl];
                     for (int i = ne - 1; i >= 0; --i) {
                         const uint64_t rec = e[i];
-                        const int64_t pos = base + (int64_t)(uint32_t)rec;
-                        while (ibw >= wa && p.own_w_q[ibw] >= slot0 && base + (int64_t)p.cb_w[ibw] >= pos) {
-                            if ((p.own_w_m[ibw] >> t) & 1) vw.step(gx, gd, base + (int64_t)p.cb_w[ibw] + 1 + (ibw - wa));
-                            --ibw;
+                        const uint32_t pos = base + (uint32_t)rec;
+                        // own detections that rank behind this event come first in the reverse sweep
+                        while (ow.valid && ow.cq >= slot0 && base + ow.ccb >= pos) {
+                            if (ow.ctp) vw.step(cw, ge, base + ow.ccb + ow.before());
+                            --ow.ib; ow.load(t);
                         }
-                        while (ibs >= sa && p.own_s_q[ibs] >= slot0 && base + (int64_t)p.cb_s[ibs] >= pos) {
-                            if ((p.own_s_m[ibs] >> t) & 1) vs.step(gx, gd, base + (int64_t)p.cb_s[ibs] + 1 + (ibs - sa));
-                            --ibs;
+                        while (os.valid && os.cq >= slot0 && base + os.ccb >= pos) {
+                            if (os.ctp) vs.step(cw, ge, base + os.ccb + os.before());
+                            --os.ib; os.load(t);
                         }
                         if ((rec >> (32 + t)) & 1ull) {
-                            vw.step(gx, gd, pos + (ibw - wa + 1));
-                            vs.step(gx, gd, pos + (ibs - sa + 1));
+                            vw.step(cw, ge, pos + ow.before());
+                            vs.step(cw, ge, pos + os.before());
                         }
                     }
-                    while (ibw >= wa && p.own_w_q[ibw] >= slot0) {
-                        if ((p.own_w_m[ibw] >> t) & 1) vw.step(gx, gd, base + (int64_t)p.cb_w[ibw] + 1 + (ibw - wa));
-                        --ibw;
+                    while (ow.valid && ow.cq >= slot0) {
+                        if (ow.ctp) vw.step(cw, ge, base + ow.ccb + ow.before());
+                        --ow.ib; ow.load(t);
                     }
-                    while (ibs >= sa && p.own_s_q[ibs] >= slot0) {
-                        if ((p.own_s_m[ibs] >> t) & 1) vs.step(gx, gd, base + (int64_t)p.cb_s[ibs] + 1 + (ibs - sa));
-                        --ibs;
+                    while (os.valid && os.cq >= slot0) {
+                        if (os.ctp) vs.step(cw, ge, base + os.ccb + os.before());
+                        --os.ib; os.load(t);
                     }
                 }
             }
             ap_w = vw.dead ? 0.0 : vw.ap;
-            ap_s = vs.dead ? 0.0 : vs.ap;
+            ap_s = same ? ap_w : (vs.dead ? 0.0 : vs.ap);
         }
     }
 #pragma unroll
@@ -462,8 +525,9 @@ extern "C" int orie_ensemble_sample(const orie_index_t *ix, int64_t t0, int64_t 
     return ORIE_OK;
 }
 
-extern "C" int orie_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
-                           void *workspace, size_t workspace_bytes, double *reward, double *detail, orie_stream_t stream) {
+static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
+                      void *workspace, size_t workspace_bytes, double *reward, double *detail, cudaStream_t stream,
+                      cudaEvent_t *marks /* 5 events or NULL */) {
     ORIE_TRY(check_range(ix, t0, nt, "orie_reward"));
     if (!ens_bits || !reward || !workspace || N < 0) {
         set_error("orie_reward: null buffer or negative N");
@@ -505,6 +569,7 @@ extern "C" int orie_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const
         spb = round_up(spb > 0 ? spb : 1, warps);
         return (int)spb;
     };
+    if (marks) ORIE_CUDA(cudaEventRecord(marks[0], stream));
     // labels
     if (ix->SL > 0) {
         WalkParams lp = wp;
@@ -515,6 +580,7 @@ extern "C" int orie_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const
         walk_kernel<false><<<grid, walk_threads, smem, stream>>>(lp);
         ORIE_LAUNCH_CHECK();
     }
+    if (marks) ORIE_CUDA(cudaEventRecord(marks[1], stream));
     // detections
     {
         wp.slot_img = ix->slot_img; wp.seg_chunk0 = ix->seg_chunk0; wp.seg_nch = ix->seg_nch;
@@ -531,6 +597,7 @@ extern "C" int orie_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const
         walk_kernel<true><<<grid, walk_threads, smem, stream>>>(wp);
         ORIE_LAUNCH_CHECK();
     }
+    if (marks) ORIE_CUDA(cudaEventRecord(marks[2], stream));
     // AP
     ApParams ap;
     memset(&ap, 0, sizeof(ap));
@@ -546,13 +613,56 @@ extern "C" int orie_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const
     ap.cb_w = (const uint32_t *)(ws + L.cb_w); ap.cb_s = (const uint32_t *)(ws + L.cb_s);
     ap.partial = (double *)(ws + L.partial);
     Grid101 grid101;
-    for (int g = 0; g <= 100; ++g) grid101.x[g] = (double)g * 0.01;   // == np.linspace(0, 1, 101) bit for bit
-    grid101.x[100] = 1.0;
-    for (int g = 0; g < 100; ++g) grid101.d[g] = grid101.x[g + 1] - grid101.x[g];
+    {
+        double x[101], w[101];
+        for (int g = 0; g <= 100; ++g) { x[g] = (double)g * 0.01; w[g] = 0.0; }   // == np.linspace(0, 1, 101) bit for bit
+        x[100] = 1.0;
+        for (int g = 0; g < 100; ++g) {
+            const double d = x[g + 1] - x[g];          // np.diff
+            w[g] += d / 2; w[g + 1] += d / 2;
+        }
+        grid101.cw[0] = grid101.cwx[0] = 0.0;
+        for (int g = 0; g <= 100; ++g) {
+            grid101.cw[g + 1] = grid101.cw[g] + w[g];
+            grid101.cwx[g + 1] = grid101.cwx[g] + w[g] * x[g];
+        }
+        for (int k = 0; k < 4; ++k) grid101.ge[k] = 0;
+        for (int g = 0; g <= 100; ++g)
+            if (x[g] >= (double)g / 100.0) grid101.ge[g >> 5] |= 1u << (g & 31);
+    }
     const int64_t items = nt * ix->class_groups;
     ap_kernel<<<(unsigned)ceil_div(items, kApThreads / 32), kApThreads, 0, stream>>>(ap, grid101);
     ORIE_LAUNCH_CHECK();
+    if (marks) ORIE_CUDA(cudaEventRecord(marks[3], stream));
     finalize_kernel<<<(unsigned)ceil_div(nt, 128), 128, 0, stream>>>(ap.partial, nt, ix->class_groups, ix->T, N, reward, detail);
     ORIE_LAUNCH_CHECK();
+    if (marks) ORIE_CUDA(cudaEventRecord(marks[4], stream));
     return ORIE_OK;
+}
+
+extern "C" int orie_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
+                           void *workspace, size_t workspace_bytes, double *reward, double *detail, orie_stream_t stream) {
+    return run_reward(ix, t0, nt, ens_bits, N, workspace, workspace_bytes, reward, detail, stream, nullptr);
+}
+
+extern "C" int orie_reward_profile(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
+                                   void *workspace, size_t workspace_bytes, double *reward, double *detail,
+                                   orie_stream_t stream, float *kernel_ms_host) {
+    if (!kernel_ms_host) {
+        set_error("orie_reward_profile: kernel_ms_host is NULL");
+        return ORIE_EINVAL;
+    }
+    cudaEvent_t marks[5];
+    for (int i = 0; i < 5; ++i) ORIE_CUDA(cudaEventCreate(&marks[i]));
+    int rc = run_reward(ix, t0, nt, ens_bits, N, workspace, workspace_bytes, reward, detail, stream, marks);
+    if (rc == ORIE_OK && nt > 0) {
+        cudaError_t e = cudaEventSynchronize(marks[4]);
+        if (e != cudaSuccess) {
+            set_error("orie_reward_profile: %s", cudaGetErrorString(e));
+            rc = ORIE_ECUDA;
+        }
+        for (int i = 0; i < 4 && rc == ORIE_OK; ++i) cudaEventElapsedTime(&kernel_ms_host[i], marks[i], marks[i + 1]);
+    }
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(marks[i]);
+    return rc;
 }

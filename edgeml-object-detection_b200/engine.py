@@ -44,37 +44,61 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_FIELDS = ("w_off", "w_box", "w_conf", "w_cls", "s_off", "s_box", "s_conf", "s_cls", "l_off", "l_box", "l_cls")
+
+
+class HostPacked:
+    """A ``Packed`` dataset staged once in pinned host memory (torch tensors)."""
+
+    def __init__(self, p: Packed):
+        self.num_images, self.num_classes = int(p.num_images), int(p.num_classes)
+        self.nbytes = p.nbytes()
+        for k in _FIELDS:
+            t = torch.from_numpy(np.ascontiguousarray(getattr(p, k)))
+            setattr(self, k, t.pin_memory() if (t.numel() and torch.cuda.is_available()) else t)
+
+
+class DevicePacked:
+    """The packed dataset resident in HBM."""
+
+    def __init__(self, p, device):
+        if isinstance(p, Packed):
+            p = HostPacked(p)
+        self.num_images, self.num_classes, self.nbytes = p.num_images, p.num_classes, p.nbytes
+        self.device = torch.device(device)
+        for k in _FIELDS:
+            setattr(self, k, getattr(p, k).to(self.device, non_blocking=True))
+
+
 class Engine:
-    def __init__(self, packed: Packed, iouv=IOU_05, device=None, seg_chunks: int = 0, stream=None):
+    def __init__(self, packed, iouv=IOU_05, device=None, seg_chunks: int = 0, stream=None):
+        """``packed``: ``Packed`` (host numpy), ``HostPacked`` (pinned) or
+        ``DevicePacked`` (already in HBM).  Uploads if needed, then runs TP
+        matching for both detectors and builds the dataset index."""
         if not torch.cuda.is_available():
             raise RuntimeError("orie_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
+        if isinstance(packed, DevicePacked) and device is None:
+            device = packed.device
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.iouv = np.ascontiguousarray(np.asarray(iouv, dtype=np.float64))
         self.T = int(len(self.iouv))
         self.M, self.Cn = int(packed.num_images), int(packed.num_classes)
         self._handle = C.c_void_p(0)
         self._ws = None
+        self._status = None
         with torch.cuda.device(self.device):
             self.stream = stream or torch.cuda.current_stream()
             with torch.cuda.stream(self.stream):
-                self._upload(packed)
+                d = packed if isinstance(packed, DevicePacked) else DevicePacked(packed, self.device)
+                self.h2d_bytes = d.nbytes
+                for k in _FIELDS:
+                    setattr(self, k, getattr(d, k))
+                self.Dw, self.Ds, self.G = int(self.w_cls.numel()), int(self.s_cls.numel()), int(self.l_cls.numel())
                 self._match()
                 self._build_index(seg_chunks)
 
     # ------------------------------------------------------------------ setup
-    def _dev(self, a: np.ndarray):
-        t = torch.from_numpy(np.ascontiguousarray(a))
-        if t.numel() == 0:
-            return torch.empty(t.shape, dtype=t.dtype, device=self.device)
-        return t.pin_memory().to(self.device, non_blocking=True)
-
-    def _upload(self, p: Packed):
-        self.h2d_bytes = p.nbytes()
-        self.w_off, self.w_box, self.w_conf, self.w_cls = map(self._dev, (p.w_off, p.w_box, p.w_conf, p.w_cls))
-        self.s_off, self.s_box, self.s_conf, self.s_cls = map(self._dev, (p.s_off, p.s_box, p.s_conf, p.s_cls))
-        self.l_off, self.l_box, self.l_cls = map(self._dev, (p.l_off, p.l_box, p.l_cls))
-        self.Dw, self.Ds, self.G = len(p.w_cls), len(p.s_cls), len(p.l_cls)
 
     def _s(self):
         return C.c_void_p(self.stream.cuda_stream)
@@ -206,8 +230,24 @@ class Engine:
             _lib.check(self.lib.orie_ensemble_sample(self._handle, t0, nt, N, int(seed) & (2**64 - 1), _ptr(bits), self._s()))
         return bits[:nt].cpu().numpy().view(np.uint32)
 
+    def profile_reward(self, num_ensemble: int, seed: int = 0, t0: int = 0, nt=None):
+        """One reward pass with CUDA events around each kernel.
+        Returns dict(label_walk_ms, walk_ms, ap_ms, finalize_ms)."""
+        nt = self.M - t0 if nt is None else int(nt)
+        N = clamp_ensemble(self.M, num_ensemble)
+        dev = self.device
+        with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            ws = self._workspace(self.workspace_bytes(nt))
+            bits = torch.empty((nt, self.info["ens_words"]), dtype=torch.int32, device=dev)
+            reward = torch.empty(nt, dtype=torch.float64, device=dev)
+            _lib.check(self.lib.orie_ensemble_sample(self._handle, t0, nt, N, int(seed) & (2**64 - 1), _ptr(bits), self._s()))
+            ms = (C.c_float * 4)()
+            _lib.check(self.lib.orie_reward_profile(self._handle, t0, nt, _ptr(bits), N, _ptr(ws), ws.numel(),
+                                                    _ptr(reward), C.c_void_p(0), self._s(), ms))
+        return dict(label_walk_ms=ms[0], walk_ms=ms[1], ap_ms=ms[2], finalize_ms=ms[3])
+
     def check_status(self):
-        st = int(self._status.item()) if getattr(self, "_status", None) is not None else 0
+        st = int(self._status.item()) if self._status is not None else 0
         if st:
             raise _lib.OrieError(5, "ensemble index out of range, equal to its target, or repeated"
                                     f" (status {st})")

@@ -65,7 +65,8 @@ int orie_version(void);
  *   tp_mask[d]   bit t set  <=> upstream's correct[d, t]
  *   match_idx[d] label row (within the image) the detection is matched to at
  *                every threshold where it is a TP; -1 if it is a TP nowhere
- *   best_iou[d]  IoU with its best same-class label (0 if none); may be NULL
+ *   best_iou[d]  IoU with its best same-class label (0 if none)
+ * All three outputs are required (best_iou doubles as the kernel's scratch).
  */
 int orie_match(const double *det_box, const int32_t *det_cls, const int64_t *det_off,
                const double *lab_box, const int32_t *lab_cls, const int64_t *lab_off,
@@ -140,6 +141,18 @@ int orie_ensemble_sample(const orie_index_t *idx, int64_t t0, int64_t nt, int64_
 size_t orie_reward_workspace_bytes(const orie_index_t *idx, int64_t nt);
 int orie_reward(const orie_index_t *idx, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
                 void *workspace, size_t workspace_bytes, double *reward, double *detail, orie_stream_t stream);
+
+/*
+ * Same as orie_reward, with CUDA events recorded on `stream` around each kernel; synchronises and
+ * writes kernel_ms_host[4] = {label walk, detection walk, AP integration, finalize} in milliseconds.
+ * Measurement aid for bench.py's roofline figure; not part of the reference-facing path.
+ */
+int orie_reward_profile(const orie_index_t *idx, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
+                        void *workspace, size_t workspace_bytes, double *reward, double *detail,
+                        orie_stream_t stream, float *kernel_ms_host);
+
+/* Number of kernels this library has launched in this process (all threads). */
+long long orie_launch_count(void);
 
 #ifdef __cplusplus
 }

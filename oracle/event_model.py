@@ -121,44 +121,72 @@ def walk_target(ix: Index, member: np.ndarray, j: int):
     return tot, events, cum[wq], cum[sq]
 
 
+GRID_C = np.array([g / 100.0 for g in range(101)])       # correctly rounded g/100
+GRID_GE = GRID >= GRID_C                                  # np.linspace's g*0.01 against it (exact-tie rule)
+# trapezoid weights per grid point: sum_g d_g (y_g + y_{g+1}) / 2 == sum_g W_g y_g
+GRID_W = np.zeros(101)
+GRID_W[:100] += GRID_D / 2
+GRID_W[1:] += GRID_D / 2
+GRID_CW = np.concatenate([[0.0], np.cumsum(GRID_W)])             # CW[i]  = sum_{g<i} W_g
+GRID_CWX = np.concatenate([[0.0], np.cumsum(GRID_W * GRID)])     # CWX[i] = sum_{g<i} W_g x_g
+
+
+def grid_lo(a, n_l):
+    """Smallest grid index g with x_g >= (a/100)/n_l in numpy's float comparison, decided in
+    integers: g*n_l > a, or == a and GRID_GE[g]."""
+    q, r = divmod(a, n_l)
+    g = q + (1 if r > 0 else 0)
+    if r == 0 and g <= 100 and not GRID_GE[g]:
+        g += 1
+    return g
+
+
 class _Var:
-    """Reverse-sweep state of one (class, threshold, variant) AP integral."""
+    """Reverse-sweep state of one (class, threshold, variant) AP integral.
+
+    Three facts make the sweep cheap (csrc/reward.cu uses the same):
+    * below the last true positive the interpolated curve is the plain precision
+      envelope: with j = p_{k+1}-1, precision k/j never exceeds (k+1)/p_{k+1}
+      (because p_{k+1} >= k+1), so np.interp's two knots carry the same value and
+      y(x) = E_{k+1} = max_{k'>k} k'/p_{k'};
+    * "x_g >= fl(k/n_l)" is decided in integers: 100*k vs g*n_l, and on exact
+      rational ties by the constant table GRID_GE.  Different rationals differ by
+      >= 1/(100 n_l), far above float64 rounding, so this equals numpy's comparison;
+    * a run of grid points that share one envelope value E contributes
+      E * (CW[hi+1] - CW[lo]) to np.trapz; only the tail beyond the last true
+      positive is a genuine linear ramp (closed form with CW and CWX).
+    Summation order differs from np.trapz by O(1e-16) relative."""
 
     def __init__(self, K, n_p, n_l):
         self.n_l = n_l
         self.ap = 0.0
-        self.g = 99
-        self.y_next = 0.0            # y at grid point 100 is always 0
+        self.g = 99                  # highest grid point not yet integrated (y at 100 is always 0)
         self.k = K
-        self.E = -1.0
+        self.kE, self.pE = 0, 1      # running envelope max as an exact fraction
         self.dead = (K == 0 or n_p == 0)
         if self.dead:
             return
-        r_k = K / n_l
-        self._consume(r_k, K / n_p, 1.0, 0.0)
-        self.r_cur = r_k
-
-    def _consume(self, r_lo, env_lo, r_hi, env_hi):
-        if self.g >= 0 and GRID[self.g] >= r_lo:
-            slope = (env_hi - env_lo) / (r_hi - r_lo)
-            while self.g >= 0 and GRID[self.g] >= r_lo:
-                x = GRID[self.g]
-                y = env_lo if x == r_lo else slope * (x - r_lo) + env_lo
-                self.ap += GRID_D[self.g] * (self.y_next + y) / 2.0
-                self.y_next = y
-                self.g -= 1
+        gl = grid_lo(K * 100, n_l)
+        if gl <= self.g:
+            r_k = K / n_l
+            env = K / n_p
+            slope = (0.0 - env) / (1.0 - r_k)
+            sw = GRID_CW[self.g + 1] - GRID_CW[gl]
+            swx = GRID_CWX[self.g + 1] - GRID_CWX[gl]
+            self.ap = slope * (swx - r_k * sw) + env * sw
+            self.g = gl - 1
 
     def step(self, pos):
         """The k-th true positive (k = self.k) sits at 1-based rank ``pos``."""
         if self.dead:
             return
         k = self.k
-        self.E = max(self.E, k / pos)
-        r_lo = (k - 1) / self.n_l
-        j = pos - 1
-        prec_j = 1.0 if j == 0 else (k - 1) / j
-        self._consume(r_lo, max(prec_j, self.E), self.r_cur, self.E)
-        self.r_cur = r_lo
+        if k * self.pE > self.kE * pos:
+            self.kE, self.pE = k, pos
+        gl = grid_lo((k - 1) * 100, self.n_l)
+        if gl <= self.g:
+            self.ap += (self.kE / self.pE) * (GRID_CW[self.g + 1] - GRID_CW[gl])
+            self.g = gl - 1
         self.k = k - 1
 
 

@@ -1,0 +1,38 @@
+"""Developer tool (not part of the product path): A/B kernel timings inside one process."""
+import os, sys, time, json
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import orie_b200  # noqa
+from orie_b200.engine import DevicePacked, Engine, HostPacked
+sys.argv = [sys.argv[0]] + sys.argv[1:]
+import bench
+
+workload = sys.argv[1] if len(sys.argv) > 1 else "coco5000"
+segs = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0,16,32,64,128".split(","))]
+ds, pk, N, iouv = bench.dataset(workload)
+dev = torch.device("cuda:0")
+hp = HostPacked(pk)
+dp = DevicePacked(hp, dev)
+torch.cuda.synchronize()
+for sc in segs:
+    eng = Engine(dp, iouv=iouv, seg_chunks=sc)
+    rows = []
+    for rep in range(6):
+        rows.append(eng.profile_reward(N, seed=rep))
+    med = {k: float(np.median([r[k] for r in rows[1:]])) for k in rows[0]}
+    print("seg_chunks", sc, eng.info["segments"], {k: round(v, 3) for k, v in med.items()}, flush=True)
+    eng.close()
+
+# e2e breakdown
+def sync():
+    torch.cuda.synchronize()
+for rep in range(6):
+    t = [time.perf_counter()]
+    d = DevicePacked(hp, dev); sync(); t.append(time.perf_counter())
+    eng = Engine(d, iouv=iouv); sync(); t.append(time.perf_counter())
+    r = eng.orie_device(N, seed=rep); sync(); t.append(time.perf_counter())
+    h = r.cpu(); sync(); t.append(time.perf_counter())
+    eng.close(); sync(); t.append(time.perf_counter())
+    print("e2e ms: h2d %.2f  match+index %.2f  reward %.2f  d2h %.2f  close %.2f" % tuple(1e3 * (b - a) for a, b in zip(t, t[1:])), flush=True)
