@@ -1,0 +1,169 @@
+"""Python call surface mirroring the reference's:
+
+    set_data(weak, strong, label)      lib/data.py:46-84   -> list-of-tuples cache
+    compute_rewards_from_dirs(...)     reward.py:72-93     -> reward vector + seconds
+    save_rewards(...)                  reward.py:90-92     -> orie{N}.npz / dcsb.npz
+
+Everything numeric runs in the CUDA engine; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import os
+import time
+from pathlib import Path
+
+import numpy as np
+
+from . import data
+from .engine import IOU_05, IOU_05_095, Engine, clamp_ensemble, shard_range
+
+
+def parse_iou_thresholds(spec) -> np.ndarray:
+    """'0.5' -> [0.5] (what the reference ships, lib/data.py:61);
+    '0.5:0.95' -> np.linspace(0.5, 0.95, 10) (the commented alternative, lib/data.py:62);
+    'a,b,c' -> explicit list."""
+    if isinstance(spec, (list, tuple, np.ndarray)):
+        return np.asarray(spec, dtype=np.float64)
+    spec = str(spec).strip()
+    if spec in ("0.5", ".5"):
+        return IOU_05.copy()
+    if spec in ("0.5:0.95", ".5:.95", "coco"):
+        return IOU_05_095.copy()
+    return np.array([float(x) for x in spec.split(",")], dtype=np.float64)
+
+
+def ensemble_matrix_numpy(num_images: int, num_ensemble: int, base_seed: int, t0: int = 0, nt=None) -> np.ndarray:
+    """The reference's draw (reward.py:35-38: arange, shift past the target,
+    ``np.random.permutation(...)[:N]``) with the legacy generator seeded by
+    ``base_seed + img_idx`` for each target — the parity mode's ensembles."""
+    nt = num_images - t0 if nt is None else nt
+    n = clamp_ensemble(num_images, num_ensemble)
+    out = np.empty((nt, n), dtype=np.int32)
+    for r in range(nt):
+        i = t0 + r
+        others = np.arange(num_images - 1)
+        if i < num_images - 1:
+            others[i:] += 1
+        out[r] = np.random.RandomState(base_seed + i).permutation(others)[:n]
+    return out
+
+
+def set_data(weak, strong, label, iouv=IOU_05, device=None):
+    """Drop-in for ``lib.data.set_data`` (same return layout):
+    ``weak_data[i] = (tp bool[n,T], conf f64[n], cls int64[n])`` (empty image:
+    ``(bool[0,T], f64[0], f64[0])``), same for strong, ``labels[i] = cls
+    int64[m]`` or an empty float array.  TP flags come from the CUDA matcher."""
+    names, lab, wk, st = data.load_dirs(weak, strong, label)
+    pk = data.pack(lab, wk, st)
+    iouv = parse_iou_thresholds(iouv)
+    eng = Engine(pk, iouv=iouv, device=device)
+    try:
+        wtp, stp, _, _ = eng.tp_flags()
+    finally:
+        eng.close()
+    T = len(iouv)
+
+    def cache(rows, tp):
+        out = []
+        for i in range(rows.num_images):
+            a, b = rows.off[i], rows.off[i + 1]
+            if a == b:
+                out.append((np.zeros((0, T), dtype=bool), np.array([]), np.array([])))
+            else:
+                out.append((tp[a:b], rows.rows[a:b, 5].copy(), rows.rows[a:b, 0].astype(int)))
+        return out
+
+    labels = [lab.rows[lab.off[i]:lab.off[i + 1], 0].astype(int) if lab.off[i + 1] > lab.off[i] else np.array([])
+              for i in range(lab.num_images)]
+    return cache(wk, wtp), cache(st, stp), labels
+
+
+def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", num_ensemble=1000, iouv=IOU_05,
+                              seed=None, ensembles="device", device=None, verbose=True):
+    """What ``reward.py:main`` does between parsing and saving.
+
+    Returns (reward ndarray, seconds, info).  ``seconds`` covers what the
+    reference's own timer covers (the reward phase, reward.py:76-88) — here the
+    index build, the ensemble draw and the reward kernels; loading and TP
+    matching are reported separately in ``info`` like upstream's ``set_data``.
+    Under torchrun (WORLD_SIZE > 1) targets are sharded over the ranks and the
+    slices are combined with one NCCL all-gather."""
+    import torch
+    method = method.lower()
+    if method == "ori":
+        method, num_ensemble = "orie", 0
+    if method not in ("orie", "dcsb"):
+        raise ValueError(f"unknown method {method!r}")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            dist.init_process_group("nccl")
+    t = time.perf_counter()
+    names, lab, wk, st = data.load_dirs(weak_dir, strong_dir, label_dir)
+    pk = data.pack(lab, wk, st)
+    t_load = time.perf_counter() - t
+    M = pk.num_images
+    if M == 0:
+        return (np.zeros(0) if method == "orie" else np.zeros(0, dtype=int)), 0.0, {"load_s": t_load}
+    iouv = parse_iou_thresholds(iouv)
+    N = num_ensemble
+    if method == "orie":
+        if N > M - 1 and verbose and rank == 0:
+            print("Ensemble size is too large. Set to the dataset size.")
+        if N < 0 and verbose and rank == 0:
+            print("Ensemble size is negative. Set to 0.")
+    if seed is None:
+        seed = int.from_bytes(os.urandom(4), "little")    # the reference is unseeded
+    if dist is not None:
+        s = torch.tensor([seed], dtype=torch.int64, device="cuda")
+        dist.broadcast(s, 0)
+        seed = int(s.item())
+    t = time.perf_counter()
+    # the same dense remap applies on every rank, so results agree across ranks
+    from .engine import HostPacked
+    eng = Engine(HostPacked(pk), iouv=iouv, device=device)
+    torch.cuda.synchronize()
+    t_match = time.perf_counter() - t
+    try:
+        start = time.perf_counter()
+        if method == "dcsb":
+            reward = eng.dcsb().astype(int)
+        else:
+            t0, nt = shard_range(M, rank, world)
+            em = ensemble_matrix_numpy(M, N, seed, t0, nt) if ensembles == "numpy" else None
+            mine = eng.orie_device(N, ens_matrix=em, seed=seed, t0=t0, nt=nt)
+            if dist is not None:
+                per = shard_range(M, 0, world)[1]
+                pad = torch.zeros(per, dtype=torch.float64, device=eng.device)
+                pad[:nt] = mine
+                out = torch.empty(per * world, dtype=torch.float64, device=eng.device)
+                eng.stream.synchronize()
+                dist.all_gather_into_tensor(out, pad)
+                reward = out[:M].cpu().numpy()
+            else:
+                reward = mine.cpu().numpy()
+            eng.check_status()
+            reward = np.where(np.isnan(reward), 0, reward)     # reward.py:86 (the kernel already stores 0)
+        seconds = time.perf_counter() - start
+        info = {"load_s": t_load, "match_index_s": t_match, "seed": seed, "images": M, "names": names,
+                "num_ensemble_used": clamp_ensemble(M, N) if method == "orie" else None, "index": dict(eng.info)}
+    finally:
+        eng.close()
+    return reward, seconds, info
+
+
+def save_rewards(save_dir, method, num_ensemble, reward, seconds):
+    """reward.py:90-92: ``orie{N}.npz`` (N as typed on the command line, not the
+    clamped value) or ``dcsb.npz`` with keys ``reward`` and ``time``."""
+    Path(save_dir).mkdir(parents=True, exist_ok=True)
+    method = method.lower()
+    if method == "ori":
+        method, num_ensemble = "orie", 0
+    file_name = f"orie{num_ensemble}.npz" if method == "orie" else "dcsb.npz"
+    path = os.path.join(save_dir, file_name)
+    np.savez(path, reward=reward, time=seconds)
+    return path

@@ -35,13 +35,24 @@ def _ref_path():
         sys.path.remove(REF_ROOT)
 
 
+_MODS = None
+
+
 def modules():
-    """(reward, lib.metrics, lib.data) of the live reference."""
-    with _ref_path():
-        import reward as ref_reward            # noqa
-        import lib.metrics as ref_metrics      # noqa
-        import lib.data as ref_data            # noqa
-    return ref_reward, ref_metrics, ref_data
+    """(reward, lib.metrics, lib.data) of the live reference.  ``reward.py`` is
+    loaded by path under the name ``_upstream_reward`` because this repository
+    has a ``reward.py`` of its own (the drop-in CLI)."""
+    global _MODS
+    if _MODS is None:
+        import importlib.util
+        with _ref_path():
+            import lib.metrics as ref_metrics      # noqa
+            import lib.data as ref_data            # noqa
+            spec = importlib.util.spec_from_file_location("_upstream_reward", os.path.join(REF_ROOT, "reward.py"))
+            ref_reward = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(ref_reward)
+        _MODS = (ref_reward, ref_metrics, ref_data)
+    return _MODS
 
 
 def ref_set_data(weak_dir, strong_dir, label_dir, iouv=None):

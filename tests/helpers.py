@@ -42,5 +42,6 @@ def flat_tp(cache, D, T):
 
 
 def make_packed(config="smoke500", M=200, seed=None, **kw):
+    """M=None keeps the configuration's own image count."""
     ds = synth.make(config, num_images=M, seed=seed, **kw)
     return ds, data.pack(ds.labels, ds.weak, ds.strong)

@@ -1,0 +1,35 @@
+"""CPU: the engine's formulation (global sort + membership + reverse AP sweep,
+oracle/event_model.py) against the straightforward oracle."""
+import numpy as np
+import pytest
+
+from helpers import O, flat_tp, make_packed, oracle_cache
+from oracle import event_model as E
+
+
+def masks(cache, D, T):
+    tp = flat_tp(cache, D, T).astype(np.int64)
+    return (tp << np.arange(T)).sum(axis=1)
+
+
+@pytest.mark.parametrize("M,N,T,segch,seed", [(36, 10, 1, 1, 1), (36, 12, 10, 2, 2), (24, 0, 10, 4, 3), (30, 29, 10, 1, 4)])
+def test_event_model_equals_oracle(M, N, T, segch, seed):
+    iouv = O.IOU_05 if T == 1 else O.IOU_05_095
+    _, pk = make_packed(M=M, seed=seed, empty_det_frac=0.06)
+    wd, sd, lc = oracle_cache(pk, iouv)
+    ix = E.build_index(M, pk.num_classes, pk.w_off, pk.w_cls.astype(np.int64), pk.w_conf, masks(wd, len(pk.w_cls), T),
+                       pk.s_off, pk.s_cls.astype(np.int64), pk.s_conf, masks(sd, len(pk.s_cls), T),
+                       pk.l_off, pk.l_cls.astype(np.int64), seg_chunks=segch)
+    em = O.ensemble_matrix(M, N, 7)
+    want = O.orie_all(wd, sd, lc, em)
+    got = np.array([E.reward_target(ix, j, em[j], T) for j in range(M)])
+    assert np.abs(got - want).max() < 1e-9
+
+
+def test_integer_recall_rule_equals_float_comparison():
+    # "x_g >= fl(k / n_l)" decided in integers (oracle/event_model.py:grid_lo) for every small case
+    for n_l in list(range(1, 260)) + [1000, 4096, 99991]:
+        ks = range(0, n_l + 1) if n_l < 300 else list(range(0, 200)) + [n_l // 2, n_l - 1, n_l]
+        for k in ks:
+            want = int(np.searchsorted(E.GRID, k / n_l, side="left"))   # first g with x_g >= k/n_l
+            assert E.grid_lo(k * 100, n_l) == want, (k, n_l)
