@@ -3,10 +3,12 @@
 //
 // reward.py:40-49 gathers N+1 cached records and lib/metrics.py:100-104 re-sorts
 // them by confidence for EVERY target.  The relative order of two detections never
-// changes between targets, so the engine sorts the weak detections of the whole
-// dataset once by (class asc, confidence desc, image, row) with the radix sort in
-// sort.cu and lays them out in "slots"; an ensemble then only selects a subset of
-// slots (reward.cu).  See DESIGN.md §3 for the layout.
+// changes between targets, so the engine sorts the detections of the whole dataset
+// once — weak and strong together, by (class asc, confidence desc, weak before
+// strong, image, row) with the radix sort in sort.cu — and lays the weak ones out in
+// "slots"; an ensemble then only selects a subset of slots (reward.cu), and a strong
+// detection's place among the weak ones is the number of weak detections sorted
+// before it.  See DESIGN.md §3 for the layout.
 #include <algorithm>
 #include <vector>
 
@@ -15,7 +17,7 @@
 namespace orie {
 
 // ----------------------------------------------------------------------------
-// small kernels
+// small kernels.  "u" is a combined detection id: [0, Dw) weak rows, [Dw, Dw+Ds) strong rows.
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t conf_desc_key(double c) {
     // order-isomorphic to "descending double": smaller key <=> larger confidence
@@ -24,11 +26,21 @@ __device__ __forceinline__ uint64_t conf_desc_key(double c) {
     return ~asc;
 }
 
+struct Dets {
+    int64_t Dw, Ds;
+    const int32_t *w_cls, *s_cls;
+    const double *w_conf, *s_conf;
+    const uint16_t *w_tp, *s_tp;
+    __device__ __forceinline__ int cls(uint32_t u) const { return u < Dw ? w_cls[u] : s_cls[u - Dw]; }
+    __device__ __forceinline__ double conf(uint32_t u) const { return u < Dw ? w_conf[u] : s_conf[u - Dw]; }
+};
+
+// image of every row of one CSR block (largest i with off[i] <= k)
 __global__ void image_of_row_kernel(const int64_t *__restrict__ off, int64_t M, int64_t n, uint32_t *__restrict__ img,
                                     int32_t *__restrict__ status) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    int64_t lo = 0, hi = M;  // largest i with off[i] <= k
+    int64_t lo = 0, hi = M;
     while (hi - lo > 1) {
         int64_t mid = (lo + hi) >> 1;
         if (off[mid] <= k) lo = mid; else hi = mid;
@@ -37,20 +49,27 @@ __global__ void image_of_row_kernel(const int64_t *__restrict__ off, int64_t M, 
     if (off[lo + 1] - off[lo] > 65535) atomicOr(status, 1);
 }
 
-__global__ void conf_keys_kernel(const double *__restrict__ conf, int64_t n, uint64_t *__restrict__ keys,
-                                 uint32_t *__restrict__ vals) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    keys[k] = conf_desc_key(conf[k]);
-    vals[k] = (uint32_t)k;
+__global__ void conf_keys_kernel(const Dets d, int64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    keys[u] = conf_desc_key(d.conf((uint32_t)u));
+    vals[u] = (uint32_t)u;
 }
 
-// keys[k] = (src[vals[k]] >> shift)
-__global__ void gather_keys_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ vals, int64_t n,
-                                   int shift, uint64_t *__restrict__ keys) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    keys[k] = (uint64_t)(src[vals[k]] >> shift);
+enum KeyKind { kKeyClass = 0, kKeyImageDetector = 1, kKeyBatchDetector = 2 };
+
+// re-key the current order for the next stable pass
+template <int KIND>
+__global__ void rekey_kernel(const Dets d, const uint32_t *__restrict__ img_all, const uint32_t *__restrict__ vals, int64_t n,
+                             uint64_t *__restrict__ keys) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t u = vals[v];
+    uint64_t k;
+    if (KIND == kKeyClass) k = (uint64_t)(uint32_t)d.cls(u);
+    else if (KIND == kKeyImageDetector) k = ((uint64_t)img_all[u] << 1) | (u >= d.Dw);
+    else k = ((uint64_t)(img_all[u] >> 5) << 1) | (u >= d.Dw);
+    keys[v] = k;
 }
 
 // class histogram: per-block shared-memory bins (C <= kHistSmemBins), flushed with one global atomic per
@@ -84,22 +103,27 @@ __global__ void fill_u32_kernel(uint32_t *__restrict__ p, int64_t n, uint32_t v)
     if (k < n) p[k] = v;
 }
 
-// rank r of the sorted weak order -> slot
-__global__ void place_slots_kernel(const uint32_t *__restrict__ order, const int32_t *__restrict__ cls,
-                                   const uint32_t *__restrict__ img, const uint16_t *__restrict__ tp,
-                                   const double *__restrict__ conf, int64_t n, const uint32_t *__restrict__ cls_off,
+__global__ void weak_flag_kernel(const uint32_t *__restrict__ order, int64_t n, uint32_t Dw, uint32_t *__restrict__ flag) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n) flag[v] = order[v] < Dw ? 1u : 0u;
+}
+
+// position v of the combined (class, conf desc) order -> slot (weak) / insertion slot (strong).
+// wpre[v] = number of weak detections sorted before v.
+__global__ void place_slots_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ wpre,
+                                   const uint32_t *__restrict__ img_all, int64_t n, const uint32_t *__restrict__ cls_off,
                                    const uint32_t *__restrict__ pad_off, uint32_t *__restrict__ slot_img,
-                                   uint16_t *__restrict__ slot_tp, uint32_t *__restrict__ prank,
-                                   double *__restrict__ conf_sorted) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const uint32_t det = order[r];
-    const int c = cls[det];
-    const uint32_t slot = pad_off[c] + ((uint32_t)r - cls_off[c]);
-    slot_img[slot] = img[det];
-    slot_tp[slot] = tp[det];
-    prank[det] = slot;
-    conf_sorted[r] = conf[det];
+                                   uint16_t *__restrict__ slot_tp, uint32_t *__restrict__ q_of_det) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t u = order[v];
+    const int c = d.cls(u);
+    const uint32_t slot = pad_off[c] + (wpre[v] - cls_off[c]);
+    q_of_det[u] = slot;       // weak: its own slot; strong: the slot it would be inserted in front of
+    if (u < d.Dw) {
+        slot_img[slot] = img_all[u];
+        slot_tp[slot] = d.w_tp[u];
+    }
 }
 
 // one warp per chunk
@@ -128,62 +152,63 @@ __global__ void gather_seg_ev0_kernel(const int32_t *__restrict__ seg_chunk0, in
     if (s < S) seg_ev0[s] = evbase[seg_chunk0[s]];
 }
 
-// insertion slot of a strong detection in the weak stream: behind every weak detection of its
-// class whose confidence is >= its own (weak first on exact ties == stable concatenation order)
-__global__ void strong_query_kernel(const int32_t *__restrict__ cls, const double *__restrict__ conf, int64_t n,
-                                    const double *__restrict__ conf_sorted, const uint32_t *__restrict__ cls_off,
-                                    const uint32_t *__restrict__ pad_off, uint32_t *__restrict__ q) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int c = cls[k];
-    const double v = conf[k];
-    const double *seg = conf_sorted + cls_off[c];
-    int lo = 0, hi = (int)(cls_off[c + 1] - cls_off[c]);  // first index with seg[i] < v
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (seg[mid] >= v) lo = mid + 1; else hi = mid;
+// Image-major order (key = image * 2 + is_strong): image i occupies [w_off[i] + s_off[i], ...), its weak
+// rows first.  Fills the own lists (aligned with w_off / s_off) and remembers each row's own position.
+__global__ void own_fill_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ img_all,
+                                int64_t n, const int64_t *__restrict__ w_off, const int64_t *__restrict__ s_off,
+                                const uint32_t *__restrict__ q_of_det, uint32_t *__restrict__ own_w_q,
+                                uint16_t *__restrict__ own_w_m, uint16_t *__restrict__ own_w_c, uint32_t *__restrict__ own_s_q,
+                                uint16_t *__restrict__ own_s_m, uint16_t *__restrict__ own_s_c, uint32_t *__restrict__ ownpos) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t u = order[v];
+    const uint32_t im = img_all[u];
+    const int64_t local = v - (w_off[im] + s_off[im]);
+    const int64_t nw = w_off[im + 1] - w_off[im];
+    if (u < d.Dw) {
+        const int64_t pos = w_off[im] + local;
+        own_w_q[pos] = q_of_det[u]; own_w_m[pos] = d.w_tp[u]; own_w_c[pos] = (uint16_t)d.w_cls[u];
+        ownpos[u] = (uint32_t)pos;
+    } else {
+        const int64_t pos = s_off[im] + (local - nw);
+        own_s_q[pos] = q_of_det[u]; own_s_m[pos] = d.s_tp[u - d.Dw]; own_s_c[pos] = (uint16_t)d.s_cls[u - d.Dw];
+        ownpos[u] = (uint32_t)pos;
     }
-    q[k] = pad_off[c] + (uint32_t)lo;
-}
-
-// own list entry i (image-major, sorted) <- detection vals[i]
-__global__ void own_fill_kernel(const uint32_t *__restrict__ vals, int64_t n, const uint32_t *__restrict__ q_of_det,
-                                const uint16_t *__restrict__ tp, uint32_t *__restrict__ own_q,
-                                uint16_t *__restrict__ own_m, uint32_t *__restrict__ ownpos_of_det) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t det = vals[i];
-    own_q[i] = q_of_det[det];
-    own_m[i] = tp[det];
-    ownpos_of_det[det] = (uint32_t)i;
 }
 
 // class start table of every image's own list: cs[img][c] = first local index with class >= c
-__global__ void own_class_start_kernel(const uint32_t *__restrict__ vals, int64_t n, const int32_t *__restrict__ cls,
-                                       const uint32_t *__restrict__ img, const int64_t *__restrict__ off, int64_t C,
-                                       uint16_t *__restrict__ cs) {
+__global__ void own_class_start_kernel(const uint16_t *__restrict__ own_c, const uint32_t *__restrict__ img_of_row, int64_t n,
+                                       const int64_t *__restrict__ off, int64_t C, uint16_t *__restrict__ cs) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t det = vals[i];
-    const uint32_t im = img[det];
-    const int c = cls[det];
+    const uint32_t im = img_of_row[i];
+    const int c = own_c[i];
     const int64_t a = off[im], b = off[im + 1];
     uint16_t *row = cs + (int64_t)im * (C + 1);
     const int local = (int)(i - a);
     if (i == a)
         for (int cc = 0; cc <= c; ++cc) row[cc] = 0;
-    const int cnext = (i + 1 < b) ? cls[vals[i + 1]] : (int)C;
+    const int cnext = (i + 1 < b) ? (int)own_c[i + 1] : (int)C;
     for (int cc = c + 1; cc <= cnext; ++cc) row[cc] = (uint16_t)(local + 1);
 }
 
-// batch-major query entry k <- detection vals[k]
-__global__ void batch_query_kernel(const uint32_t *__restrict__ vals, int64_t n, const uint32_t *__restrict__ q_of_det,
-                                   const uint32_t *__restrict__ img, const uint32_t *__restrict__ ownpos_of_det,
-                                   uint2 *__restrict__ bq) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const uint32_t det = vals[k];
-    bq[k] = make_uint2(q_of_det[det], ((img[det] & 31u) << 27) | ownpos_of_det[det]);
+// Batch-major order (key = (image / 32) * 2 + is_strong): batch b occupies [w_off[32b] + s_off[32b], ...),
+// its weak rows first, each part ascending by query slot.
+__global__ void batch_query_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ img_all,
+                                   int64_t n, int64_t M, const int64_t *__restrict__ w_off, const int64_t *__restrict__ s_off,
+                                   const uint32_t *__restrict__ q_of_det, const uint32_t *__restrict__ ownpos,
+                                   uint2 *__restrict__ bq_w, uint2 *__restrict__ bq_s) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t u = order[v];
+    const uint32_t im = img_all[u];
+    const int64_t i0 = (int64_t)(im >> 5) * 32;
+    const int64_t i1 = i0 + 32 < M ? i0 + 32 : M;
+    const int64_t local = v - (w_off[i0] + s_off[i0]);
+    const int64_t nw = w_off[i1] - w_off[i0];
+    const uint2 e = make_uint2(q_of_det[u], ((im & 31u) << 27) | ownpos[u]);
+    if (u < d.Dw) bq_w[w_off[i0] + local] = e;
+    else bq_s[s_off[i0] + (local - nw)] = e;
 }
 
 // bqoff[b][s] = first entry of batch b with q >= first slot of segment s  (s == S: end of the batch)
@@ -239,6 +264,7 @@ struct Builder {
     cudaStream_t st;
     std::vector<void *> temps;
     ~Builder() {
+        cudaStreamSynchronize(st);
         for (void *p : temps) cudaFreeAsync(p, st);
     }
     template <typename Tp>
@@ -313,8 +339,16 @@ static int upload(Builder &B, Tp **dst, const std::vector<Tp> &src, bool keep) {
 static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                  const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
                  const int64_t *l_off, const int32_t *l_cls, int seg_chunks_req, cudaStream_t st) {
-    Builder B{ix, st};
+    // host staging buffers are declared before the Builder so that they outlive its destructor, which
+    // synchronises the stream (asynchronous copies from / into them may still be in flight on error paths)
     const int64_t M = ix->M, C = ix->C;
+    std::vector<uint32_t> h_hist(2 * C);
+    std::vector<int32_t> cls_order(C);
+    StreamLayout LD, LL;
+    int32_t h_status = 0;
+    uint32_t h_total = 0;
+    int64_t tails[3];
+    Builder B{ix, st};
     {
         int dev = 0;
         cudaMemPool_t pool;
@@ -324,7 +358,6 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         ORIE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
     }
     // ---- sizes (three small D2H reads)
-    int64_t tails[3];
     ORIE_CUDA(cudaMemcpyAsync(&tails[0], w_off + M, 8, cudaMemcpyDeviceToHost, st));
     ORIE_CUDA(cudaMemcpyAsync(&tails[1], s_off + M, 8, cudaMemcpyDeviceToHost, st));
     ORIE_CUDA(cudaMemcpyAsync(&tails[2], l_off + M, 8, cudaMemcpyDeviceToHost, st));
@@ -335,7 +368,9 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
                   (long long)Dw, (long long)Ds, (long long)G);
         return ORIE_ELIMIT;
     }
-    const int64_t Dmax = std::max(std::max(Dw, Ds), std::max<int64_t>(G, 1));
+    const int64_t n = Dw + Ds;
+    const int64_t Nmax = std::max<int64_t>(std::max(n, G), 1);
+    const Dets dets{Dw, Ds, w_cls, s_cls, w_conf, s_conf, w_tp, s_tp};
 
     ORIE_TRY(B.keep(&ix->w_off, M + 1));
     ORIE_TRY(B.keep(&ix->s_off, M + 1));
@@ -344,77 +379,69 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
 
     // ---- temporaries
     uint64_t *keys, *keys_tmp;
-    uint32_t *vals, *vals_tmp, *img_w, *img_s, *img_l, *order_w, *order_s, *hist, *prank, *q_s, *ownpos, *evcnt;
-    uint16_t *slot_tp;
-    double *conf_sorted;
+    uint32_t *vals, *vals_tmp, *img_all, *img_l, *order, *hist, *wpre, *q_of_det, *ownpos, *evcnt, *d_total;
+    uint16_t *slot_tp, *own_w_c, *own_s_c;
     int32_t *status;
-    void *rscratch;
-    ORIE_TRY(B.temp(&keys, Dmax));
-    ORIE_TRY(B.temp(&keys_tmp, Dmax));
-    ORIE_TRY(B.temp(&vals, Dmax));
-    ORIE_TRY(B.temp(&vals_tmp, Dmax));
-    ORIE_TRY(B.temp(&img_w, Dw));
-    ORIE_TRY(B.temp(&img_s, Ds));
+    char *rscratch, *sscratch;
+    ORIE_TRY(B.temp(&keys, Nmax));
+    ORIE_TRY(B.temp(&keys_tmp, Nmax));
+    ORIE_TRY(B.temp(&vals, Nmax));
+    ORIE_TRY(B.temp(&vals_tmp, Nmax));
+    ORIE_TRY(B.temp(&img_all, n));
     ORIE_TRY(B.temp(&img_l, G));
-    ORIE_TRY(B.temp(&order_w, Dw));
-    ORIE_TRY(B.temp(&order_s, Ds));
+    ORIE_TRY(B.temp(&order, n));
     ORIE_TRY(B.temp(&hist, 3 * C));
-    ORIE_TRY(B.temp(&prank, Dw));
-    ORIE_TRY(B.temp(&q_s, Ds));
-    ORIE_TRY(B.temp(&ownpos, std::max(Dw, Ds)));
-    ORIE_TRY(B.temp(&conf_sorted, Dw));
+    ORIE_TRY(B.temp(&wpre, n));
+    ORIE_TRY(B.temp(&q_of_det, n));
+    ORIE_TRY(B.temp(&ownpos, n));
+    ORIE_TRY(B.temp(&own_w_c, Dw));
+    ORIE_TRY(B.temp(&own_s_c, Ds));
     ORIE_TRY(B.temp(&status, 1));
-    {
-        char *p;
-        ORIE_TRY(B.temp(&p, (int64_t)radix_scratch_bytes(Dmax)));
-        rscratch = p;
-    }
+    ORIE_TRY(B.temp(&d_total, 1));
+    ORIE_TRY(B.temp(&rscratch, (int64_t)radix_scratch_bytes(Nmax)));
+    ORIE_TRY(B.temp(&sscratch, (int64_t)scan_scratch_bytes(Nmax)));
     ORIE_CUDA(cudaMemsetAsync(status, 0, 4, st));
     ORIE_CUDA(cudaMemsetAsync(hist, 0, (size_t)(3 * C) * 4, st));
 
-    const int cbits = bits_for(C), ibits = bits_for(M), bbits = bits_for(ix->nbatch);
+    const int cbits = bits_for(C), ibits = bits_for(M) + 1, bbits = bits_for(ix->nbatch) + 1;
 
-    // ---- image of every row; class histograms
+    // ---- image of every row; class histograms (weak / labels drive the layouts, strong is range-checked)
     const size_t hist_smem = C <= kHistSmemBins ? (size_t)C * 4 : 0;
     if (Dw) {
-        image_of_row_kernel<<<grid_for(Dw), 256, 0, st>>>(w_off, M, Dw, img_w, status);
+        image_of_row_kernel<<<grid_for(Dw), 256, 0, st>>>(w_off, M, Dw, img_all, status);
+        ORIE_LAUNCH_CHECK();
+        class_hist_kernel<<<grid_for(Dw, kHistItemsPerBlock), 256, hist_smem, st>>>(w_cls, Dw, C, hist, status);
         ORIE_LAUNCH_CHECK();
     }
     if (Ds) {
-        image_of_row_kernel<<<grid_for(Ds), 256, 0, st>>>(s_off, M, Ds, img_s, status);
+        image_of_row_kernel<<<grid_for(Ds), 256, 0, st>>>(s_off, M, Ds, img_all + Dw, status);
+        ORIE_LAUNCH_CHECK();
+        class_hist_kernel<<<grid_for(Ds, kHistItemsPerBlock), 256, hist_smem, st>>>(s_cls, Ds, C, hist + 2 * C, status);
         ORIE_LAUNCH_CHECK();
     }
     if (G) {
         image_of_row_kernel<<<grid_for(G), 256, 0, st>>>(l_off, M, G, img_l, status);
         ORIE_LAUNCH_CHECK();
-    }
-    if (Dw) {
-        class_hist_kernel<<<grid_for(Dw, kHistItemsPerBlock), 256, hist_smem, st>>>(w_cls, Dw, C, hist, status);
-        ORIE_LAUNCH_CHECK();
-    }
-    if (G) {
         class_hist_kernel<<<grid_for(G, kHistItemsPerBlock), 256, hist_smem, st>>>(l_cls, G, C, hist + C, status);
         ORIE_LAUNCH_CHECK();
     }
-    if (Ds) {
-        class_hist_kernel<<<grid_for(Ds, kHistItemsPerBlock), 256, hist_smem, st>>>(s_cls, Ds, C, hist + 2 * C, status);  // range check
-        ORIE_LAUNCH_CHECK();
-    }
 
-    // ---- global weak order: confidence desc (64-bit key), then class (stable)
-    if (Dw) {
-        conf_keys_kernel<<<grid_for(Dw), 256, 0, st>>>(w_conf, Dw, keys, vals);
+    // ---- ONE sort of all detections: confidence desc (64-bit key), then class (stable).  Weak rows precede
+    //      strong rows in the input, so on exact confidence ties weak sorts first (stable concatenation order).
+    if (n) {
+        conf_keys_kernel<<<grid_for(n), 256, 0, st>>>(dets, n, keys, vals);
         ORIE_LAUNCH_CHECK();
-        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, Dw, 0, 64, rscratch, st));
-        gather_keys_kernel<<<grid_for(Dw), 256, 0, st>>>((const uint32_t *)w_cls, vals, Dw, 0, keys);
+        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 0, 64, rscratch, st));
+        rekey_kernel<kKeyClass><<<grid_for(n), 256, 0, st>>>(dets, img_all, vals, n, keys);
         ORIE_LAUNCH_CHECK();
-        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, Dw, 0, cbits, rscratch, st));
-        ORIE_CUDA(cudaMemcpyAsync(order_w, vals, (size_t)Dw * 4, cudaMemcpyDeviceToDevice, st));
+        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 0, cbits, rscratch, st));
+        ORIE_CUDA(cudaMemcpyAsync(order, vals, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        weak_flag_kernel<<<grid_for(n), 256, 0, st>>>(order, n, (uint32_t)Dw, wpre);
+        ORIE_LAUNCH_CHECK();
+        ORIE_TRY(exclusive_scan_u32(wpre, wpre, n, nullptr, sscratch, st));
     }
 
     // ---- host: class counts -> padded layouts and segment tables
-    std::vector<uint32_t> h_hist(2 * C);
-    int32_t h_status = 0;
     ORIE_CUDA(cudaMemcpyAsync(h_hist.data(), hist, (size_t)(2 * C) * 4, cudaMemcpyDeviceToHost, st));
     ORIE_CUDA(cudaMemcpyAsync(&h_status, status, 4, cudaMemcpyDeviceToHost, st));
     ORIE_CUDA(cudaStreamSynchronize(st));
@@ -435,14 +462,16 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     int seg_chunks = seg_chunks_req > 0 ? seg_chunks_req
                                         : (int)std::min<int64_t>(512, std::max<int64_t>(16, ceil_div(raw_chunks, seg_target)));
     ix->seg_chunks = seg_chunks;
-    StreamLayout LD = make_layout(h_hist.data(), C, 1, seg_chunks);
-    StreamLayout LL = make_layout(h_hist.data() + C, C, 0, seg_chunks);
+    LD = make_layout(h_hist.data(), C, 1, seg_chunks);
+    LL = make_layout(h_hist.data() + C, C, 0, seg_chunks);
     ix->P = LD.P; ix->nchunks = LD.P / kChunk; ix->S = (int64_t)LD.seg_chunk0.size();
     ix->PL = LL.P; ix->nchunksL = LL.P / kChunk; ix->SL = (int64_t)LL.seg_chunk0.size();
     if (ix->P >= ((int64_t)1 << 31)) {
         set_error("orie_index_build: %lld slots exceed 2^31-1", (long long)ix->P);
         return ORIE_ELIMIT;
     }
+    for (int64_t c = 0; c < C; ++c) cls_order[c] = (int32_t)c;
+    std::stable_sort(cls_order.begin(), cls_order.end(), [&](int32_t a, int32_t b) { return h_hist[a] > h_hist[b]; });
     uint32_t *d_cls_off, *d_pad_off, *d_lcls_off, *d_lpad_off;
     ORIE_TRY(upload(B, &d_cls_off, LD.cls_off, false));
     ORIE_TRY(upload(B, &d_pad_off, LD.pad_off, false));
@@ -451,13 +480,13 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     ORIE_TRY(upload(B, &ix->seg_chunk0, LD.seg_chunk0, true));
     ORIE_TRY(upload(B, &ix->seg_nch, LD.seg_nch, true));
     ORIE_TRY(upload(B, &ix->cls_seg0, LD.cls_seg0, true));
+    ORIE_TRY(upload(B, &ix->cls_order, cls_order, true));
     ORIE_TRY(upload(B, &ix->lseg_chunk0, LL.seg_chunk0, true));
     ORIE_TRY(upload(B, &ix->lseg_nch, LL.seg_nch, true));
     ORIE_TRY(upload(B, &ix->lcls_seg0, LL.cls_seg0, true));
-    // the vectors must outlive the async copies
-    ORIE_CUDA(cudaStreamSynchronize(st));
+    // the host vectors stay alive until the end of this function, which ends with a stream synchronisation
 
-    // ---- slots
+    // ---- slots, strong insertion slots
     ORIE_TRY(B.keep(&ix->slot_img, ix->P));
     ORIE_TRY(B.temp(&slot_tp, ix->P));
     ORIE_TRY(B.temp(&evcnt, ix->nchunks));
@@ -467,46 +496,24 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     fill_u32_kernel<<<grid_for(ix->P), 256, 0, st>>>(ix->slot_img, ix->P, (uint32_t)M);
     ORIE_LAUNCH_CHECK();
     ORIE_CUDA(cudaMemsetAsync(slot_tp, 0, (size_t)ix->P * 2, st));
-    if (Dw) {
-        place_slots_kernel<<<grid_for(Dw), 256, 0, st>>>(order_w, w_cls, img_w, w_tp, w_conf, Dw, d_cls_off, d_pad_off,
-                                                       ix->slot_img, slot_tp, prank, conf_sorted);
+    if (n) {
+        place_slots_kernel<<<grid_for(n), 256, 0, st>>>(dets, order, wpre, img_all, n, d_cls_off, d_pad_off, ix->slot_img,
+                                                      slot_tp, q_of_det);
         ORIE_LAUNCH_CHECK();
     }
 
-    // ---- events
-    uint32_t *d_total;
-    ORIE_TRY(B.temp(&d_total, 1));
+    // ---- events (the total is read back together with the final synchronisation; evmask is sized by its bound)
     event_bits_kernel<<<grid_for(ix->nchunks * 32), 256, 0, st>>>(slot_tp, ix->nchunks, ix->evbits, evcnt);
     ORIE_LAUNCH_CHECK();
-    {
-        char *sscr;
-        ORIE_TRY(B.temp(&sscr, (int64_t)scan_scratch_bytes(ix->nchunks)));
-        ORIE_TRY(exclusive_scan_u32(evcnt, ix->evbase, ix->nchunks, d_total, sscr, st));
-    }
-    uint32_t h_total = 0;
+    ORIE_TRY(exclusive_scan_u32(evcnt, ix->evbase, ix->nchunks, d_total, sscratch, st));
     ORIE_CUDA(cudaMemcpyAsync(&h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
-    ORIE_CUDA(cudaStreamSynchronize(st));
-    ix->Ev = h_total;
-    ORIE_TRY(B.keep(&ix->evmask, ix->Ev));
+    ORIE_TRY(B.keep(&ix->evmask, Dw));             // events <= weak detections
     event_mask_kernel<<<grid_for(ix->nchunks * 32), 256, 0, st>>>(slot_tp, ix->nchunks, ix->evbits, ix->evbase, ix->evmask);
     ORIE_LAUNCH_CHECK();
     gather_seg_ev0_kernel<<<grid_for(ix->S), 256, 0, st>>>(ix->seg_chunk0, ix->S, ix->evbase, ix->seg_ev0);
     ORIE_LAUNCH_CHECK();
 
-    // ---- strong: insertion slots, global (class, conf desc) order
-    if (Ds) {
-        strong_query_kernel<<<grid_for(Ds), 256, 0, st>>>(s_cls, s_conf, Ds, conf_sorted, d_cls_off, d_pad_off, q_s);
-        ORIE_LAUNCH_CHECK();
-        conf_keys_kernel<<<grid_for(Ds), 256, 0, st>>>(s_conf, Ds, keys, vals);
-        ORIE_LAUNCH_CHECK();
-        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, Ds, 0, 64, rscratch, st));
-        gather_keys_kernel<<<grid_for(Ds), 256, 0, st>>>((const uint32_t *)s_cls, vals, Ds, 0, keys);
-        ORIE_LAUNCH_CHECK();
-        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, Ds, 0, cbits, rscratch, st));
-        ORIE_CUDA(cudaMemcpyAsync(order_s, vals, (size_t)Ds * 4, cudaMemcpyDeviceToDevice, st));
-    }
-
-    // ---- own lists and batch query lists, both detectors
+    // ---- own lists (image-major) and batch query lists (batch-major), both detectors in one pass each
     ORIE_TRY(B.keep(&ix->own_w_q, Dw));
     ORIE_TRY(B.keep(&ix->own_w_m, Dw));
     ORIE_TRY(B.keep(&ix->own_s_q, Ds));
@@ -519,41 +526,36 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     ORIE_TRY(B.keep(&ix->bqoff_s, ix->nbatch * (ix->S + 1)));
     ORIE_CUDA(cudaMemsetAsync(ix->own_w_cs, 0, (size_t)(M * (C + 1)) * 2, st));
     ORIE_CUDA(cudaMemsetAsync(ix->own_s_cs, 0, (size_t)(M * (C + 1)) * 2, st));
-    struct Det {
-        int64_t n;
-        const uint32_t *order, *img, *q;
-        const int32_t *cls;
-        const uint16_t *tp;
-        const int64_t *off;
-        uint32_t *own_q;
-        uint16_t *own_m, *own_cs;
-        uint2 *bq;
-        uint32_t *bqoff;
-    } dets[2] = {{Dw, order_w, img_w, prank, w_cls, w_tp, ix->w_off, ix->own_w_q, ix->own_w_m, ix->own_w_cs, ix->bq_w, ix->bqoff_w},
-                 {Ds, order_s, img_s, q_s, s_cls, s_tp, ix->s_off, ix->own_s_q, ix->own_s_m, ix->own_s_cs, ix->bq_s, ix->bqoff_s}};
-    for (const Det &d : dets) {
-        if (d.n) {
-            // image-major: stable sort of the global order by image
-            ORIE_CUDA(cudaMemcpyAsync(vals, d.order, (size_t)d.n * 4, cudaMemcpyDeviceToDevice, st));
-            gather_keys_kernel<<<grid_for(d.n), 256, 0, st>>>(d.img, vals, d.n, 0, keys);
-            ORIE_LAUNCH_CHECK();
-            ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, d.n, 0, ibits, rscratch, st));
-            own_fill_kernel<<<grid_for(d.n), 256, 0, st>>>(vals, d.n, d.q, d.tp, d.own_q, d.own_m, ownpos);
-            ORIE_LAUNCH_CHECK();
-            own_class_start_kernel<<<grid_for(d.n), 256, 0, st>>>(vals, d.n, d.cls, d.img, d.off, C, d.own_cs);
-            ORIE_LAUNCH_CHECK();
-            // batch-major: stable sort of the global order by image / 32
-            ORIE_CUDA(cudaMemcpyAsync(vals, d.order, (size_t)d.n * 4, cudaMemcpyDeviceToDevice, st));
-            gather_keys_kernel<<<grid_for(d.n), 256, 0, st>>>(d.img, vals, d.n, 5, keys);
-            ORIE_LAUNCH_CHECK();
-            ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, d.n, 0, bbits, rscratch, st));
-            batch_query_kernel<<<grid_for(d.n), 256, 0, st>>>(vals, d.n, d.q, d.img, ownpos, d.bq);
+    if (n) {
+        ORIE_CUDA(cudaMemcpyAsync(vals, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        rekey_kernel<kKeyImageDetector><<<grid_for(n), 256, 0, st>>>(dets, img_all, vals, n, keys);
+        ORIE_LAUNCH_CHECK();
+        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 0, ibits, rscratch, st));
+        own_fill_kernel<<<grid_for(n), 256, 0, st>>>(dets, vals, img_all, n, ix->w_off, ix->s_off, q_of_det, ix->own_w_q,
+                                                   ix->own_w_m, own_w_c, ix->own_s_q, ix->own_s_m, own_s_c, ownpos);
+        ORIE_LAUNCH_CHECK();
+        if (Dw) {
+            own_class_start_kernel<<<grid_for(Dw), 256, 0, st>>>(own_w_c, img_all, Dw, ix->w_off, C, ix->own_w_cs);
             ORIE_LAUNCH_CHECK();
         }
-        batch_query_offsets_kernel<<<grid_for(ix->nbatch * (ix->S + 1)), 256, 0, st>>>(d.bq, d.off, M, ix->nbatch,
-                                                                                     ix->seg_chunk0, ix->S, d.bqoff);
+        if (Ds) {
+            own_class_start_kernel<<<grid_for(Ds), 256, 0, st>>>(own_s_c, img_all + Dw, Ds, ix->s_off, C, ix->own_s_cs);
+            ORIE_LAUNCH_CHECK();
+        }
+        ORIE_CUDA(cudaMemcpyAsync(vals, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        rekey_kernel<kKeyBatchDetector><<<grid_for(n), 256, 0, st>>>(dets, img_all, vals, n, keys);
+        ORIE_LAUNCH_CHECK();
+        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 0, bbits, rscratch, st));
+        batch_query_kernel<<<grid_for(n), 256, 0, st>>>(dets, vals, img_all, n, M, ix->w_off, ix->s_off, q_of_det, ownpos,
+                                                      ix->bq_w, ix->bq_s);
         ORIE_LAUNCH_CHECK();
     }
+    batch_query_offsets_kernel<<<grid_for(ix->nbatch * (ix->S + 1)), 256, 0, st>>>(ix->bq_w, ix->w_off, M, ix->nbatch,
+                                                                                 ix->seg_chunk0, ix->S, ix->bqoff_w);
+    ORIE_LAUNCH_CHECK();
+    batch_query_offsets_kernel<<<grid_for(ix->nbatch * (ix->S + 1)), 256, 0, st>>>(ix->bq_s, ix->s_off, M, ix->nbatch,
+                                                                                 ix->seg_chunk0, ix->S, ix->bqoff_s);
+    ORIE_LAUNCH_CHECK();
 
     // ---- label stream
     ORIE_TRY(B.keep(&ix->lab_slot_img, ix->PL));
@@ -571,6 +573,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         ORIE_LAUNCH_CHECK();
     }
     ORIE_CUDA(cudaStreamSynchronize(st));
+    ix->Ev = h_total;
     return ORIE_OK;
 }
 

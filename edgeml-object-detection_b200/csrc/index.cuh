@@ -21,6 +21,7 @@ struct orie_index {
     int32_t *seg_nch = nullptr;      // [S]
     uint32_t *seg_ev0 = nullptr;     // [S] evbase[seg_chunk0[s]]
     int32_t *cls_seg0 = nullptr;     // [C+1]
+    int32_t *cls_order = nullptr;    // [C] classes by descending weak-detection count (AP warps take neighbours)
 
     // ---- per-batch query lists: the own detections of a batch's 32 images, ascending by query slot
     uint2 *bq_w = nullptr;           // [Dw] {q, lane << 27 | own position}

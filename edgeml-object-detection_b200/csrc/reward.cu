@@ -214,7 +214,7 @@ walk_kernel(const WalkParams p) {
 struct Grid101 {
     double cw[102];   // cw[i]  = sum_{g<i} W_g,      W = trapezoid weight of grid point g of np.linspace(0,1,101)
     double cwx[102];  // cwx[i] = sum_{g<i} W_g x_g
-    uint32_t ge[4];   // bit g: x[g] >= correctly rounded g/100 (decides exact rational ties, see ApVar)
+    uint32_t ge[5];   // bit g: x[g] >= correctly rounded g/100 (decides exact rational ties, see ApVar); ge[4]: all set
 };
 
 struct ApParams {
@@ -222,7 +222,7 @@ struct ApParams {
     int T, cls_per_warp;
     int64_t class_groups;
     int64_t S, SL, Ev;
-    const int32_t *cls_seg0, *seg_chunk0, *lcls_seg0;
+    const int32_t *cls_seg0, *seg_chunk0, *lcls_seg0, *cls_order;
     const uint32_t *seg_ev0;
     const uint32_t *tot, *evcnt, *totL;
     const uint64_t *ev;
@@ -236,57 +236,50 @@ struct ApParams {
 // Reverse-sweep state of one (class, threshold, variant) AP integral; oracle/event_model.py:_Var
 // is the CPU statement of the same thing and carries the argument for the three shortcuts:
 //  * below the last true positive np.interp's two knots carry the same envelope value, so the
-//    curve is y(x) = E = max_{k' > k} k'/p_{k'}; E is kept as an exact fraction (kE/pE) and only
-//    divided when a run of grid points actually samples it;
-//  * "x_g >= fl(k/n_l)" is decided in integers (100 k vs g n_l; exact ties by the constant ge table);
+//    curve is y(x) = E = max_{k' > k} k'/p_{k'};
+//  * "x_g >= fl(k/n_l)" is decided in integers: 100 k = q n_l + r, first grid point = q + (r > 0)
+//    (exact ties by the constant ge table); q, r are updated incrementally as k decreases;
 //  * a run of grid points sharing one E contributes E * (cw[hi+1] - cw[lo]) to np.trapz; only the
 //    tail beyond the last true positive is a genuine linear ramp (lib/metrics.py:137-144), integrated
 //    in closed form with cw and cwx.
 // 1/p to ~1 ulp without the IEEE division sequence: float seed + two Newton steps.  Only used for
-// envelope values that are multiplied into the integral (tolerance 1e-9 on mAP), never for a comparison.
+// envelope values that are multiplied into the integral (tolerance 1e-9 on mAP), never for a branch
+// that changes which grid points are sampled.
 __device__ __forceinline__ double fast_ratio(uint32_t num, uint32_t den) {
     const double d = (double)den;
-    double r = (double)__frcp_rn((float)den);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));     // MUFU.RCP64H: ~20 good bits
     r = __fma_rn(r, __fma_rn(-d, r, 1.0), r);
     r = __fma_rn(r, __fma_rn(-d, r, 1.0), r);
     return __dmul_rn((double)num, r);
 }
 
 struct ApVar {
-    double ap;
-    float inv_nl;
-    uint32_t kE, pE, k, n_l;
+    double ap, E;
+    uint32_t k, n_l;
+    int q, r;             // 100 * k == q * n_l + r, 0 <= r < n_l   (k = true positives still in front)
+    int dq, dr;           // 100 == dq * n_l + dr
     int g;                // highest grid point not yet integrated
     bool dead;
 
-    // smallest g with x_g >= (k100/100)/n_l in numpy's float comparison; k100 = 100 * (number of TPs)
-    __device__ __forceinline__ int grid_lo(const uint32_t *ge, uint64_t a) const {
-        int gl;
-        bool tie;
-        if (n_l < (1u << 25)) {                 // a <= 100 n_l < 2^32: 32-bit path
-            const uint32_t a32 = (uint32_t)a;
-            int q = (int)((float)a32 * inv_nl);                 // floor(a / n_l) within +-1
-            int r = (int)(a32 - (uint32_t)q * n_l);
-            if (r < 0) { --q; r += (int)n_l; }
-            else if (r >= (int)n_l) { ++q; r -= (int)n_l; }
-            gl = q + (r > 0);
-            tie = r == 0;
-        } else {
-            const uint64_t q = a / n_l;
-            const uint64_t r = a - q * n_l;
-            gl = (int)q + (r > 0);
-            tie = r == 0;
-        }
-        if (tie && gl <= 100 && !((ge[gl >> 5] >> (gl & 31)) & 1u)) ++gl;
+    // ge[4] == 1 (set by the host when every bit of the tie table is set, which holds for np.linspace's grid):
+    // an exact tie always counts as "reached" and the table lookup is skipped
+    __device__ __forceinline__ int first_grid(const uint32_t *ge) const {
+        int gl = q + (r > 0);
+        if (!ge[4] && r == 0 && gl <= 100 && !((ge[gl >> 5] >> (gl & 31)) & 1u)) ++gl;
         return gl;
     }
     __device__ __forceinline__ void init(const double *cw, const double *cwx, const uint32_t *ge, uint32_t K, uint32_t n_p,
                                          uint32_t nl) {
-        ap = 0.0; g = 99; k = K; kE = 0; pE = 1; n_l = nl;
-        inv_nl = 1.0f / (float)nl;
+        ap = 0.0; E = 0.0; g = 99; k = K; n_l = nl; q = 0; r = 0;
         dead = (K == 0 || n_p == 0);
         if (dead) return;
-        const int gl = grid_lo(ge, (uint64_t)K * 100ull);
+        const uint64_t a = (uint64_t)K * 100ull;
+        q = (int)(a / nl);
+        r = (int)(a - (uint64_t)q * nl);
+        dq = (int)(100u / nl);
+        dr = (int)(100u - (uint32_t)dq * nl);
+        const int gl = first_grid(ge);
         if (gl <= g) {
             const double r_k = __ddiv_rn((double)K, (double)nl);
             const double env = __ddiv_rn((double)K, (double)n_p);
@@ -300,13 +293,16 @@ struct ApVar {
     // the k-th true positive (k = current k) sits at 1-based rank pos
     __device__ __forceinline__ void step(const double *cw, const uint32_t *ge, uint32_t pos) {
         if (dead) return;
-        if ((uint64_t)k * pE > (uint64_t)kE * pos) { kE = k; pE = pos; }
-        const int gl = grid_lo(ge, (uint64_t)(k - 1) * 100ull);
+        E = fmax(E, fast_ratio(k, pos));
+        --k;
+        q -= dq;
+        r -= dr;
+        if (r < 0) { r += (int)n_l; --q; }
+        const int gl = first_grid(ge);
         if (gl <= g) {
-            ap = __dadd_rn(ap, __dmul_rn(fast_ratio(kE, pE), __dsub_rn(cw[g + 1], cw[gl])));
+            ap = __dadd_rn(ap, __dmul_rn(E, __dsub_rn(cw[g + 1], cw[gl])));
             g = gl - 1;
         }
-        --k;
     }
 };
 
@@ -315,18 +311,27 @@ struct ApVar {
 struct OwnCursor {
     const uint32_t *q, *cb;
     const uint16_t *m;
-    int64_t ib, lo;
+    int ib, lo;           // indices relative to the image's own list
     uint32_t cq, ccb;
     bool ctp, valid;
     __device__ __forceinline__ void load(int t) {
         valid = ib >= lo;
         if (valid) { cq = q[ib]; ccb = cb[ib]; ctp = (m[ib] >> t) & 1; }
     }
-    __device__ __forceinline__ void init(const uint32_t *q_, const uint32_t *cb_, const uint16_t *m_, int64_t lo_, int64_t hi_, int t) {
+    __device__ __forceinline__ void init(const uint32_t *q_, const uint32_t *cb_, const uint16_t *m_, int lo_, int hi_, int t) {
         q = q_; cb = cb_; m = m_; lo = lo_; ib = hi_ - 1; cq = 0; ccb = 0; ctp = false;
         load(t);
     }
     __device__ __forceinline__ uint32_t before() const { return (uint32_t)(ib - lo + 1); }   // own entries still in front
+    // own detections of the current segment that rank behind position `pos` (pos == 0: all of the segment's)
+    __device__ __forceinline__ void drain(ApVar &v, const double *cw, const uint32_t *ge, uint32_t base, uint32_t slot0,
+                                          uint32_t pos, int t) {
+        while (valid && cq >= slot0 && base + ccb >= pos) {
+            if (ctp) v.step(cw, ge, base + ccb + before());
+            --ib;
+            load(t);
+        }
+    }
 };
 
 constexpr int kApThreads = 128;
@@ -335,39 +340,44 @@ __global__ void __launch_bounds__(kApThreads, 8)
 ap_kernel(const ApParams p, const Grid101 grid) {
     __shared__ double cw[102];
     __shared__ double cwx[102];
-    __shared__ uint32_t ge[4];
+    __shared__ uint32_t ge[5];
     for (int i = threadIdx.x; i < 102; i += kApThreads) { cw[i] = grid.cw[i]; cwx[i] = grid.cwx[i]; }
-    if (threadIdx.x < 4) ge[threadIdx.x] = grid.ge[threadIdx.x];
+    if (threadIdx.x < 5) ge[threadIdx.x] = grid.ge[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t item = (int64_t)blockIdx.x * (kApThreads / 32) + (threadIdx.x >> 5);
     if (item >= p.nt * p.class_groups) return;
     const int64_t tl = item / p.class_groups, grp = item % p.class_groups;
     const int slot = lane / p.T, t = lane % p.T;
-    const int64_t c = grp * p.cls_per_warp + slot;
-    const bool active = slot < p.cls_per_warp && c < p.C;
+    const int64_t ci = grp * p.cls_per_warp + slot;
+    const bool active = slot < p.cls_per_warp && ci < p.C;
     const int64_t j = p.t0 + tl;
 
     double ap_w = 0.0, ap_s = 0.0, has_gt = 0.0;
     if (active) {
+        const int c = p.cls_order[ci];          // classes of similar size share a warp
         uint32_t n_l = p.gtcnt[j * p.C + c];
         for (int ls = p.lcls_seg0[c]; ls < p.lcls_seg0[c + 1]; ++ls) n_l += p.totL[(int64_t)ls * p.ntp + tl];
         if (n_l > 0) {
             if (t == 0) has_gt = 1.0;
             const int s0 = p.cls_seg0[c], s1 = p.cls_seg0[c + 1];
             const uint64_t *ev = p.ev + tl * p.Ev;
+            const uint32_t *tot = p.tot + tl, *evcnt = p.evcnt + tl;
             uint32_t n_ens = 0, K_ens = 0;
             for (int s = s0; s < s1; ++s) {
-                n_ens += p.tot[(int64_t)s * p.ntp + tl];
+                n_ens += tot[(int64_t)s * p.ntp];
                 const uint64_t *e = ev + p.seg_ev0[s];
-                const int ne = (int)p.evcnt[(int64_t)s * p.ntp + tl];
+                const int ne = (int)evcnt[(int64_t)s * p.ntp];
                 for (int i = 0; i < ne; ++i) K_ens += (uint32_t)((e[i] >> (32 + t)) & 1ull);
             }
-            const int64_t wa = p.w_off[j] + p.own_w_cs[j * (p.C + 1) + c], wb = p.w_off[j] + p.own_w_cs[j * (p.C + 1) + c + 1];
-            const int64_t sa = p.s_off[j] + p.own_s_cs[j * (p.C + 1) + c], sb = p.s_off[j] + p.own_s_cs[j * (p.C + 1) + c + 1];
+            const uint16_t *wcs = p.own_w_cs + j * (p.C + 1) + c, *scs = p.own_s_cs + j * (p.C + 1) + c;
+            const int wa = wcs[0], wb = wcs[1], sa = scs[0], sb = scs[1];
+            const uint32_t *wq = p.own_w_q + p.w_off[j], *wcb = p.cb_w + p.w_off[j];
+            const uint32_t *sq = p.own_s_q + p.s_off[j], *scb = p.cb_s + p.s_off[j];
+            const uint16_t *wm = p.own_w_m + p.w_off[j], *sm = p.own_s_m + p.s_off[j];
             uint32_t K_w = K_ens, K_s = K_ens;
-            for (int64_t i = wa; i < wb; ++i) K_w += (p.own_w_m[i] >> t) & 1;
-            for (int64_t i = sa; i < sb; ++i) K_s += (p.own_s_m[i] >> t) & 1;
+            for (int i = wa; i < wb; ++i) K_w += (wm[i] >> t) & 1;
+            for (int i = sa; i < sb; ++i) K_s += (sm[i] >> t) & 1;
             ApVar vw, vs;
             vw.init(cw, cwx, ge, K_w, n_ens + (uint32_t)(wb - wa), n_l);
             vs.init(cw, cwx, ge, K_s, n_ens + (uint32_t)(sb - sa), n_l);
@@ -376,40 +386,37 @@ ap_kernel(const ApParams p, const Grid101 grid) {
             if (same) vs.dead = true;
             if (!(vw.dead && vs.dead)) {
                 OwnCursor ow, os;
-                ow.init(p.own_w_q, p.cb_w, p.own_w_m, wa, wb, t);
-                os.init(p.own_s_q, p.cb_s, p.own_s_m, sa, sb, t);
-                uint32_t rem = n_ens;
-                for (int s = s1 - 1; s >= s0; --s) {
-                    rem -= p.tot[(int64_t)s * p.ntp + tl];
-                    const uint32_t base = rem;
-                    const uint32_t slot0 = (uint32_t)p.seg_chunk0[s] * 32u;
-                    const uint64_t *e = ev + p.seg_ev0[s];
-                    const int ne = (int)p.evcnt[(int64_t)s * p.ntp + tl];
-                    for (int i = ne - 1; i >= 0; --i) {
-                        const uint64_t rec = e[i];
-                        const uint32_t pos = base + (uint32_t)rec;
-                        // own detections that rank behind this event come first in the reverse sweep
-                        while (ow.valid && ow.cq >= slot0 && base + ow.ccb >= pos) {
-                            if (ow.ctp) vw.step(cw, ge, base + ow.ccb + ow.before());
-                            --ow.ib; ow.load(t);
+                ow.init(wq, wcb, wm, wa, wb, t);
+                os.init(sq, scb, sm, sa, sb, t);
+                // one flat loop over (segment, event) pairs, last to first, so that lanes working on classes
+                // with different segment structure do not wait for each other at segment boundaries
+                int s = s1, i = -1;
+                uint32_t base = n_ens, slot0 = 0;
+                const uint64_t *e = ev;
+                for (;;) {
+                    if (i < 0) {
+                        if (s < s1) {                       // leaving a segment: its remaining own detections
+                            ow.drain(vw, cw, ge, base, slot0, 0u, t);
+                            os.drain(vs, cw, ge, base, slot0, 0u, t);
                         }
-                        while (os.valid && os.cq >= slot0 && base + os.ccb >= pos) {
-                            if (os.ctp) vs.step(cw, ge, base + os.ccb + os.before());
-                            --os.ib; os.load(t);
-                        }
-                        if ((rec >> (32 + t)) & 1ull) {
-                            vw.step(cw, ge, pos + ow.before());
-                            vs.step(cw, ge, pos + os.before());
-                        }
+                        if (s == s0) break;
+                        --s;
+                        base -= tot[(int64_t)s * p.ntp];
+                        slot0 = (uint32_t)p.seg_chunk0[s] * 32u;
+                        e = ev + p.seg_ev0[s];
+                        i = (int)evcnt[(int64_t)s * p.ntp] - 1;
+                        continue;
                     }
-                    while (ow.valid && ow.cq >= slot0) {
-                        if (ow.ctp) vw.step(cw, ge, base + ow.ccb + ow.before());
-                        --ow.ib; ow.load(t);
+                    const uint64_t rec = e[i];
+                    const uint32_t pos = base + (uint32_t)rec;
+                    // own detections that rank behind this event come first in the reverse sweep
+                    ow.drain(vw, cw, ge, base, slot0, pos, t);
+                    os.drain(vs, cw, ge, base, slot0, pos, t);
+                    if ((rec >> (32 + t)) & 1ull) {
+                        vw.step(cw, ge, pos + ow.before());
+                        vs.step(cw, ge, pos + os.before());
                     }
-                    while (os.valid && os.cq >= slot0) {
-                        if (os.ctp) vs.step(cw, ge, base + os.ccb + os.before());
-                        --os.ib; os.load(t);
-                    }
+                    --i;
                 }
             }
             ap_w = vw.dead ? 0.0 : vw.ap;
@@ -604,7 +611,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     ap.M = ix->M; ap.C = ix->C; ap.nt = nt; ap.ntp = ntp; ap.t0 = t0;
     ap.T = ix->T; ap.cls_per_warp = ix->cls_per_warp; ap.class_groups = ix->class_groups;
     ap.S = ix->S; ap.SL = ix->SL; ap.Ev = ix->Ev;
-    ap.cls_seg0 = ix->cls_seg0; ap.seg_chunk0 = ix->seg_chunk0; ap.lcls_seg0 = ix->lcls_seg0; ap.seg_ev0 = ix->seg_ev0;
+    ap.cls_order = ix->cls_order; ap.cls_seg0 = ix->cls_seg0; ap.seg_chunk0 = ix->seg_chunk0; ap.lcls_seg0 = ix->lcls_seg0; ap.seg_ev0 = ix->seg_ev0;
     ap.tot = (const uint32_t *)(ws + L.tot); ap.evcnt = (const uint32_t *)(ws + L.evcnt);
     ap.totL = (const uint32_t *)(ws + L.totL); ap.ev = (const uint64_t *)(ws + L.ev);
     ap.gtcnt = ix->gtcnt; ap.w_off = ix->w_off; ap.s_off = ix->s_off;
@@ -629,6 +636,8 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         for (int k = 0; k < 4; ++k) grid101.ge[k] = 0;
         for (int g = 0; g <= 100; ++g)
             if (x[g] >= (double)g / 100.0) grid101.ge[g >> 5] |= 1u << (g & 31);
+        grid101.ge[4] = (grid101.ge[0] == 0xffffffffu && grid101.ge[1] == 0xffffffffu && grid101.ge[2] == 0xffffffffu &&
+                         grid101.ge[3] == 0x1fu) ? 1u : 0u;
     }
     const int64_t items = nt * ix->class_groups;
     ap_kernel<<<(unsigned)ceil_div(items, kApThreads / 32), kApThreads, 0, stream>>>(ap, grid101);

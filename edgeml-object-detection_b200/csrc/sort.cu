@@ -96,69 +96,91 @@ int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *t
 }
 
 // ----------------------------------------------------------------------------
-// radix sort (8-bit digits, stable)
+// radix sort (8-bit digits, stable): three launches per pass
+//   radix_hist_kernel     per-block digit counts            hist[block][digit]
+//   radix_offsets_kernel  one block: digit-major exclusive offsets over (digit, block), in place
+//   radix_scatter_kernel  stable scatter
 // ----------------------------------------------------------------------------
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortSteps = 8;                       // 32-item steps per warp
-constexpr int kSortTile = kSortThreads * kSortSteps;  // 2048 items per block
+constexpr int kSortSteps = 16;                      // 32-item steps per warp
+constexpr int kSortTile = kSortThreads * kSortSteps;  // 4096 items per block
 
 __device__ __forceinline__ int digit_of(uint64_t key, int shift, uint32_t mask) {
     return (int)((uint32_t)(key >> shift) & mask);
 }
 
-// hist[digit * nblocks + block] = number of items of this block with that digit
 __global__ void __launch_bounds__(kSortThreads)
-radix_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint32_t mask,
-                  uint32_t *__restrict__ hist, int nblocks) {
+radix_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint32_t mask, uint32_t *__restrict__ hist) {
     __shared__ uint32_t h[kRadix];
-    for (int i = threadIdx.x; i < kRadix; i += kSortThreads) h[i] = 0;
+    h[threadIdx.x] = 0;
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * kSortTile;
-#pragma unroll
+#pragma unroll 4
     for (int s = 0; s < kSortSteps; ++s) {
         int64_t k = base + s * kSortThreads + threadIdx.x;
         if (k < n) atomicAdd(&h[digit_of(keys[k], shift, mask)], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kRadix; i += kSortThreads) hist[(int64_t)i * nblocks + blockIdx.x] = h[i];
+    hist[(int64_t)blockIdx.x * kRadix + threadIdx.x] = h[threadIdx.x];
 }
 
-// Stable scatter.  Warp w of a block owns items [w*256, (w+1)*256) of the tile,
-// walked in 8 steps of 32 consecutive items; __match_any_sync ranks equal digits
-// inside a step, per-warp digit counters carry the rank across steps and warps.
+// thread d owns digit d: running sum over blocks (coalesced rows), block scan of the digit totals
+__global__ void __launch_bounds__(kRadix)
+radix_offsets_kernel(uint32_t *__restrict__ hist, int nblocks) {
+    __shared__ uint32_t warp_sums[kRadix / 32];
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    uint32_t total = 0;
+    for (int b = 0; b < nblocks; ++b) total += hist[(int64_t)b * kRadix + d];
+    uint32_t incl = total;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+        uint32_t y = __shfl_up_sync(kFull, incl, k);
+        if (lane >= k) incl += y;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t base = incl - total;
+    for (int w = 0; w < warp; ++w) base += warp_sums[w];
+    for (int b = 0; b < nblocks; ++b) {
+        const uint32_t c = hist[(int64_t)b * kRadix + d];
+        hist[(int64_t)b * kRadix + d] = base;
+        base += c;
+    }
+}
+
+// Stable scatter.  Warp w of a block owns items [w*512, (w+1)*512) of the tile, walked in 16 steps of 32
+// consecutive items; __match_any_sync ranks equal digits inside a step, per-warp digit counters carry the
+// rank across steps and warps.
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                      uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
-                     int shift, uint32_t mask, const uint32_t *__restrict__ offs, int nblocks) {
+                     int shift, uint32_t mask, const uint32_t *__restrict__ offs) {
     __shared__ uint32_t cnt[kSortWarps][kRadix];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
     __syncthreads();
     const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * (32 * kSortSteps);
     uint64_t k[kSortSteps];
-    uint32_t v[kSortSteps];
-    int dg[kSortSteps];
 #pragma unroll
     for (int s = 0; s < kSortSteps; ++s) {
-        int64_t i = wbase + s * 32 + lane;
-        bool ok = i < n;
+        const int64_t i = wbase + s * 32 + lane;
+        const bool ok = i < n;
         k[s] = ok ? keys[i] : 0ull;
-        v[s] = ok ? vals[i] : 0u;
-        dg[s] = ok ? digit_of(k[s], shift, mask) : kRadix;
-        unsigned peers = __match_any_sync(kFull, dg[s]);
-        if (ok && lane == (__ffs(peers) - 1)) cnt[warp][dg[s]] += __popc(peers);
+        const int dg = ok ? digit_of(k[s], shift, mask) : kRadix;
+        const unsigned peers = __match_any_sync(kFull, dg);
+        if (ok && lane == (__ffs(peers) - 1)) cnt[warp][dg] += __popc(peers);
         __syncwarp();
     }
     __syncthreads();
     {
         const int d = threadIdx.x;  // kSortThreads == kRadix
-        uint32_t run = offs[(int64_t)d * nblocks + blockIdx.x];
+        uint32_t run = offs[(int64_t)blockIdx.x * kRadix + d];
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
-            uint32_t c = cnt[w][d];
+            const uint32_t c = cnt[w][d];
             cnt[w][d] = run;
             run += c;
         }
@@ -166,15 +188,17 @@ radix_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restri
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < kSortSteps; ++s) {
-        bool ok = dg[s] < kRadix;
-        unsigned peers = __match_any_sync(kFull, dg[s]);
+        const int64_t i = wbase + s * 32 + lane;
+        const bool ok = i < n;
+        const int dg = ok ? digit_of(k[s], shift, mask) : kRadix;
+        const unsigned peers = __match_any_sync(kFull, dg);
         uint32_t pos = 0;
-        if (ok) pos = cnt[warp][dg[s]] + __popc(peers & ((1u << lane) - 1u));
+        if (ok) pos = cnt[warp][dg] + __popc(peers & ((1u << lane) - 1u));
         __syncwarp();
         if (ok) {
             keys_out[pos] = k[s];
-            vals_out[pos] = v[s];
-            if (lane == (__ffs(peers) - 1)) cnt[warp][dg[s]] += __popc(peers);
+            vals_out[pos] = vals[i];
+            if (lane == (__ffs(peers) - 1)) cnt[warp][dg] += __popc(peers);
         }
         __syncwarp();
     }
@@ -184,8 +208,7 @@ static_assert(kSortThreads == kRadix, "one thread per digit in the carry pass");
 
 size_t radix_scratch_bytes(int64_t n) {
     int64_t nblocks = ceil_div(n > 0 ? n : 1, kSortTile);
-    int64_t h = nblocks * kRadix;
-    return round_up(h * 4, 256) + scan_scratch_bytes(h);
+    return (size_t)round_up(nblocks * kRadix * 4, 256);
 }
 
 int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
@@ -197,16 +220,16 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_
     }
     const int nblocks = (int)ceil_div(n, kSortTile);
     uint32_t *hist = (uint32_t *)scratch;
-    void *scan_scratch = (char *)scratch + round_up((int64_t)nblocks * kRadix * 4, 256);
     uint64_t *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
     for (int lo = bit_lo; lo < bit_hi; lo += kRadixBits) {
         const int bits = (bit_hi - lo) < kRadixBits ? (bit_hi - lo) : kRadixBits;
         const uint32_t mask = (1u << bits) - 1u;
-        radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, n, lo, mask, hist, nblocks);
+        radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, n, lo, mask, hist);
         ORIE_LAUNCH_CHECK();
-        ORIE_TRY(exclusive_scan_u32(hist, hist, (int64_t)nblocks * kRadix, nullptr, scan_scratch, st));
-        radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, lo, mask, hist, nblocks);
+        radix_offsets_kernel<<<1, kRadix, 0, st>>>(hist, nblocks);
+        ORIE_LAUNCH_CHECK();
+        radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, lo, mask, hist);
         ORIE_LAUNCH_CHECK();
         uint64_t *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;

@@ -162,11 +162,13 @@ class _Var:
         self.ap = 0.0
         self.g = 99                  # highest grid point not yet integrated (y at 100 is always 0)
         self.k = K
-        self.kE, self.pE = 0, 1      # running envelope max as an exact fraction
+        self.E = 0.0                 # running envelope max
         self.dead = (K == 0 or n_p == 0)
         if self.dead:
             return
-        gl = grid_lo(K * 100, n_l)
+        self.q, self.r = divmod(K * 100, n_l)     # 100 k == q n_l + r, updated incrementally below
+        gl = self._first_grid()
+        assert gl == grid_lo(K * 100, n_l)
         if gl <= self.g:
             r_k = K / n_l
             env = K / n_p
@@ -176,18 +178,27 @@ class _Var:
             self.ap = slope * (swx - r_k * sw) + env * sw
             self.g = gl - 1
 
+    def _first_grid(self):
+        gl = self.q + (1 if self.r > 0 else 0)
+        if self.r == 0 and gl <= 100 and not GRID_GE[gl]:
+            gl += 1
+        return gl
+
     def step(self, pos):
         """The k-th true positive (k = self.k) sits at 1-based rank ``pos``."""
         if self.dead:
             return
-        k = self.k
-        if k * self.pE > self.kE * pos:
-            self.kE, self.pE = k, pos
-        gl = grid_lo((k - 1) * 100, self.n_l)
+        self.E = max(self.E, self.k / pos)
+        self.k -= 1
+        self.r -= 100
+        while self.r < 0:
+            self.r += self.n_l
+            self.q -= 1
+        gl = self._first_grid()
+        assert gl == grid_lo(self.k * 100, self.n_l)
         if gl <= self.g:
-            self.ap += (self.kE / self.pE) * (GRID_CW[self.g + 1] - GRID_CW[gl])
+            self.ap += self.E * (GRID_CW[self.g + 1] - GRID_CW[gl])
             self.g = gl - 1
-        self.k = k - 1
 
 
 def ap_reverse(ix, c, t, tot, events, own, n_l):
