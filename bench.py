@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=32, help="targets in the single-thread CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seg-chunks", type=int, default=0, help="segment length override (0 = engine default)")
+    ap.add_argument("--workspace-gb", type=int, default=16, help="reward-pass workspace budget; targets run in waves that fit")
     return ap.parse_args()
 
 
@@ -245,17 +246,22 @@ def run_b200(args):
         e0.record()
         eng = Engine(dp, iouv=iouv, seg_chunks=args.seg_chunks)
         e1.record()
-        ws = eng._workspace(eng.workspace_bytes(nt))
-        bits = torch.empty((max(nt, 1), eng.info["ens_words"]), dtype=torch.int32, device=dev)
+        wave = eng.wave_size(nt, args.workspace_gb << 30) if nt > 0 else 0
+        ws = eng._workspace(eng.workspace_bytes(wave))
+        bits = torch.empty((max(wave, 1), eng.info["ens_words"]), dtype=torch.int32, device=dev)
         mine = torch.zeros(per, dtype=torch.float64, device=dev)
         import ctypes as C
         s = C.c_void_p(eng.stream.cuda_stream)
-        ms = (C.c_float * 4)()
-        if nt > 0:
-            _lib.check(lib.orie_ensemble_sample(eng._handle, t0, nt, N if N < M else M - 1, seed, C.c_void_p(bits.data_ptr()), s))
-            _lib.check(lib.orie_reward_profile(eng._handle, t0, nt, C.c_void_p(bits.data_ptr()), min(N, M - 1),
-                                               C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(mine.data_ptr()),
-                                               C.c_void_p(0), s, ms))
+        ms = [0.0] * 4
+        Nc = min(N, M - 1)
+        for a in range(0, nt, max(wave, 1)):            # target waves sized by the workspace budget
+            cnt = min(wave, nt - a)
+            part = (C.c_float * 4)()
+            _lib.check(lib.orie_ensemble_sample(eng._handle, t0 + a, cnt, Nc, seed, C.c_void_p(bits.data_ptr()), s))
+            _lib.check(lib.orie_reward_profile(eng._handle, t0 + a, cnt, C.c_void_p(bits.data_ptr()), Nc,
+                                               C.c_void_p(ws.data_ptr()), ws.numel(),
+                                               C.c_void_p(mine.data_ptr() + 8 * a), C.c_void_p(0), s, part))
+            ms = [x + float(y) for x, y in zip(ms, part)]
         if world > 1:
             dist.all_gather_into_tensor(gathered, mine)
         else:

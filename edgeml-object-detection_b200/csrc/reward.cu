@@ -19,6 +19,8 @@
 //
 // All arithmetic that decides a branch or a reward digit is IEEE float64 in upstream's order
 // (explicit _rn intrinsics; the library is built with -fmad=false).
+#include <stdlib.h>
+
 #include "index.cuh"
 
 namespace orie {
@@ -27,15 +29,26 @@ namespace orie {
 // 32x32 bit-matrix transpose across a warp: in  = row `lane`, bit c = column c
 //                                            out = column `lane`, bit r = row r
 // ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const uint32_t m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
-        const uint32_t y = __shfl_xor_sync(kFull, x, s);
-        x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
+// 13 instructions: the 16- and 8-bit stages are one byte permute each (PRMT with a per-lane selector),
+// the 4/2/1-bit stages one rotate by a per-lane amount and one bit-select (LOP3) each.
+struct Transposer {
+    uint32_t sel16, sel8, sh4, sh2, sh1, mk4, mk2, mk1;
+    __device__ __forceinline__ void init(int lane) {
+        sel16 = (lane & 16) ? 0x3276u : 0x5410u;
+        sel8 = (lane & 8) ? 0x3715u : 0x6240u;
+        sh4 = (lane & 4) ? 28u : 4u;  mk4 = (lane & 4) ? 0xf0f0f0f0u : 0x0f0f0f0fu;
+        sh2 = (lane & 2) ? 30u : 2u;  mk2 = (lane & 2) ? 0xccccccccu : 0x33333333u;
+        sh1 = (lane & 1) ? 31u : 1u;  mk1 = (lane & 1) ? 0xaaaaaaaau : 0x55555555u;
     }
-    return x;
-}
+    __device__ __forceinline__ uint32_t operator()(uint32_t x) const {
+        x = __byte_perm(x, __shfl_xor_sync(kFull, x, 16), sel16);
+        x = __byte_perm(x, __shfl_xor_sync(kFull, x, 8), sel8);
+        uint32_t y = __shfl_xor_sync(kFull, x, 4); y = __funnelshift_l(y, y, sh4); x = (x & mk4) | (y & ~mk4);
+        y = __shfl_xor_sync(kFull, x, 2); y = __funnelshift_l(y, y, sh2); x = (x & mk2) | (y & ~mk2);
+        y = __shfl_xor_sync(kFull, x, 1); y = __funnelshift_l(y, y, sh1); x = (x & mk1) | (y & ~mk1);
+        return x;
+    }
+};
 
 // ----------------------------------------------------------------------------
 // ensembles
@@ -69,13 +82,23 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 // One warp per target.  Draws `want` distinct images != target into the target's bitmap
 // (32 candidates per round, duplicates inside a round resolved by lane order, quota cut in lane
 // order), then complements the bitmap when the ensemble is more than half of the dataset.
-__global__ void ens_sample_kernel(int64_t nt, int64_t N, int64_t t0, int64_t M, int64_t words, uint64_t seed,
-                                  uint32_t *__restrict__ bits_all) {
-    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// The bitmap is built in shared memory (SMEM = true, one row per warp) or directly in global memory.
+constexpr int kSampleWarps = 4;
+template <bool SMEM>
+__global__ void __launch_bounds__(kSampleWarps * 32)
+ens_sample_kernel(int64_t nt, int64_t N, int64_t t0, int64_t M, int64_t words, uint64_t seed,
+                  uint32_t *__restrict__ bits_all) {
+    extern __shared__ uint32_t sbits[];
+    const int64_t r = (int64_t)blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
     if (r >= nt) return;
     const int lane = threadIdx.x & 31;
     const int64_t target = t0 + r;
-    uint32_t *bits = bits_all + r * words;
+    uint32_t *out = bits_all + r * words;
+    uint32_t *bits = SMEM ? sbits + (int64_t)(threadIdx.x >> 5) * words : out;
+    if (SMEM) {
+        for (int64_t w = lane; w < words; w += 32) bits[w] = 0u;
+        __syncwarp();
+    }
     const int64_t others = M - 1;
     const bool complement = 2 * N > others;
     const int64_t want = complement ? others - N : N;
@@ -96,15 +119,16 @@ __global__ void ens_sample_kernel(int64_t nt, int64_t N, int64_t t0, int64_t M, 
         __syncwarp();
         have += __popc(acc);
     }
-    if (complement) {
-        __syncwarp();
-        for (int64_t w = lane; w < words; w += 32) {
-            uint32_t v = ~*(volatile uint32_t *)&bits[w];
+    __syncwarp();
+    for (int64_t w = lane; w < words; w += 32) {
+        uint32_t v = *(volatile uint32_t *)&bits[w];
+        if (complement) {
+            v = ~v;
             const int64_t lo = w * 32;
             if (lo + 32 > M) v &= (M > lo) ? ((M - lo >= 32) ? 0xffffffffu : ((1u << (M - lo)) - 1u)) : 0u;
             if ((target >> 5) == w) v &= ~(1u << (target & 31));
-            bits[w] = v;
         }
+        if (SMEM || complement) out[w] = v;
     }
 }
 
@@ -133,22 +157,25 @@ struct WalkParams {
     uint32_t *cb_w, *cb_s;
 };
 
-constexpr int kWalkMaxThreads = 1024;
 
-template <bool DETS>
-__global__ void __launch_bounds__(kWalkMaxThreads)
+// THREADS is the block size the kernel is launched with (256 / 512 / 1024, chosen from the size of the
+// membership table); the register cap keeps 1536+ threads resident per SM.
+template <bool DETS, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1536 / THREADS > 0 ? 1536 / THREADS : 1)
 walk_kernel(const WalkParams p) {
     extern __shared__ uint32_t memb[];   // [ens_words * 32]: bit j of memb[img] = img in ensemble of target 32*batch+j
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kWarps = blockDim.x >> 5;
     const int64_t lb = blockIdx.x;                 // local batch
     const int64_t tl = lb * 32 + lane;             // local target of this lane
+    Transposer transpose;
+    transpose.init(lane);
     {
         const uint32_t *row = p.ens_bits + tl * p.ens_words;
         const bool live = tl < p.nt;
         for (int64_t w = warp; w < p.ens_words; w += kWarps) {
             const uint32_t x = live ? row[w] : 0u;
-            memb[w * 32 + lane] = transpose32(x, lane);
+            memb[w * 32 + lane] = transpose(x);
         }
     }
     __syncthreads();
@@ -172,22 +199,32 @@ walk_kernel(const WalkParams p) {
             if (qw < qw_end) nqw = p.bq_w[qw];
             if (qs < qs_end) nqs = p.bq_s[qs];
         }
+        const uint32_t *simg = p.slot_img + ch0 * 32 + lane;
+        uint32_t img_next = simg[0];               // software pipeline: the next chunk's images are in flight
+        uint32_t ebv = 0;                          // event bits of 32 chunks, one per lane
         for (int c = 0; c < nch; ++c) {
-            const int64_t ch = ch0 + c;
-            const uint32_t img = p.slot_img[ch * 32 + lane];
-            const uint32_t word = transpose32(memb[img], lane);   // bit l: slot l holds a member of MY target
+            const uint32_t img = img_next;
+            if (c + 1 < nch) img_next = simg[(int64_t)(c + 1) * 32];
+            uint32_t eb = 0, mymask = 0;
             if (DETS) {
-                uint32_t eb = p.evbits[ch];
+                if ((c & 31) == 0) ebv = (c + lane < nch) ? p.evbits[ch0 + c + lane] : 0u;
+                eb = __shfl_sync(kFull, ebv, c & 31);
+                if (lane < __popc(eb)) mymask = p.evmask[ev_i + lane];   // this chunk's event masks, one per lane
+            }
+            const uint32_t word = transpose(memb[img]);   // bit l: slot l holds a member of MY target
+            if (DETS) {
+                int e = 0;
                 while (eb) {
                     const int b = __ffs(eb) - 1;
                     eb &= eb - 1;
-                    const uint32_t mask = p.evmask[ev_i++];
+                    const uint32_t mask = __shfl_sync(kFull, mymask, e++);
                     if ((word >> b) & 1u) {
                         const uint32_t rank = cnt + __popc(word & ((2u << b) - 1u));   // 1-based, inclusive
                         evout[ecur++] = (uint64_t)rank | ((uint64_t)mask << 32);
                     }
                 }
-                const uint32_t chunk_end = (uint32_t)(ch + 1) * 32u;
+                ev_i += e;
+                const uint32_t chunk_end = (uint32_t)(ch0 + c + 1) * 32u;
                 while (nqw.x < chunk_end) {                     // uniform: own weak detections in this chunk
                     if (lane == (int)(nqw.y >> 27))
                         p.cb_w[nqw.y & 0x07ffffffu] = cnt + __popc(word & ((1u << (nqw.x & 31u)) - 1u));
@@ -526,10 +563,29 @@ extern "C" int orie_ensemble_sample(const orie_index_t *ix, int64_t t0, int64_t 
         return ORIE_EINVAL;
     }
     if (nt == 0) return ORIE_OK;
-    ORIE_CUDA(cudaMemsetAsync(ens_bits, 0, (size_t)(nt * ix->ens_words) * 4, stream));
-    ens_sample_kernel<<<(unsigned)ceil_div(nt * 32, 128), 128, 0, stream>>>(nt, N, t0, ix->M, ix->ens_words, seed, ens_bits);
+    const size_t smem = (size_t)kSampleWarps * ix->ens_words * 4;
+    const unsigned grid = (unsigned)ceil_div(nt, kSampleWarps);
+    if (smem <= 48 * 1024) {
+        ens_sample_kernel<true><<<grid, kSampleWarps * 32, smem, stream>>>(nt, N, t0, ix->M, ix->ens_words, seed, ens_bits);
+    } else {
+        ORIE_CUDA(cudaMemsetAsync(ens_bits, 0, (size_t)(nt * ix->ens_words) * 4, stream));
+        ens_sample_kernel<false><<<grid, kSampleWarps * 32, 0, stream>>>(nt, N, t0, ix->M, ix->ens_words, seed, ens_bits);
+    }
     ORIE_LAUNCH_CHECK();
     return ORIE_OK;
+}
+
+template <bool DETS, int THREADS>
+static int launch_walk_t(dim3 grid, size_t smem, cudaStream_t stream, const WalkParams &p) {
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<DETS, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    walk_kernel<DETS, THREADS><<<grid, THREADS, smem, stream>>>(p);
+    return ORIE_OK;
+}
+template <bool DETS>
+static int launch_walk(dim3 grid, int threads, size_t smem, cudaStream_t stream, const WalkParams &p) {
+    if (threads == 256) return launch_walk_t<DETS, 256>(grid, smem, stream, p);
+    if (threads == 512) return launch_walk_t<DETS, 512>(grid, smem, stream, p);
+    return launch_walk_t<DETS, 1024>(grid, smem, stream, p);
 }
 
 static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
@@ -559,8 +615,6 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         return ORIE_ELIMIT;
     }
     static_assert(sizeof(WalkParams) < 4000 && sizeof(ApParams) + sizeof(Grid101) < 4000, "kernel parameter space");
-    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     WalkParams wp;
     memset(&wp, 0, sizeof(wp));
@@ -569,8 +623,12 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     const int64_t nb = ntp / 32;
     const int walk_threads = smem <= 56 * 1024 ? 256 : smem <= 112 * 1024 ? 512 : 1024;   // keep the SM full of warps
     auto segs_per_block = [&](int64_t S) {
-        // enough blocks for >= 4 waves of 148 SMs when the data allows, at least one segment per warp
-        int64_t want_y = ceil_div(4 * 148, nb);
+        // enough blocks for two full waves of resident blocks (2048 threads per SM) when the data allows,
+        // at least one segment per warp
+        const int64_t resident = 148 * (1536 / walk_threads > 0 ? 1536 / walk_threads : 1);
+        const char *tune = getenv("ORIE_WALK_WAVES");          // developer knob (profiles/tune.py)
+        const double waves = tune ? atof(tune) : 2.0;
+        int64_t want_y = (int64_t)((waves * (double)resident + (double)nb - 1.0) / (double)nb);
         int64_t spb = ceil_div(S, want_y > 0 ? want_y : 1);
         const int64_t warps = walk_threads / 32;
         spb = round_up(spb > 0 ? spb : 1, warps);
@@ -584,7 +642,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         lp.S = ix->SL; lp.segs_per_block = segs_per_block(ix->SL);
         lp.tot = (uint32_t *)(ws + L.totL);
         dim3 grid((unsigned)nb, (unsigned)ceil_div(ix->SL, lp.segs_per_block));
-        walk_kernel<false><<<grid, walk_threads, smem, stream>>>(lp);
+        ORIE_TRY(launch_walk<false>(grid, walk_threads, smem, stream, lp));
         ORIE_LAUNCH_CHECK();
     }
     if (marks) ORIE_CUDA(cudaEventRecord(marks[1], stream));
@@ -601,7 +659,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         wp.cb_w = (uint32_t *)(ws + L.cb_w);
         wp.cb_s = (uint32_t *)(ws + L.cb_s);
         dim3 grid((unsigned)nb, (unsigned)ceil_div(ix->S, wp.segs_per_block));
-        walk_kernel<true><<<grid, walk_threads, smem, stream>>>(wp);
+        ORIE_TRY(launch_walk<true>(grid, walk_threads, smem, stream, wp));
         ORIE_LAUNCH_CHECK();
     }
     if (marks) ORIE_CUDA(cudaEventRecord(marks[2], stream));

@@ -127,12 +127,14 @@ radix_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint3
     hist[(int64_t)blockIdx.x * kRadix + threadIdx.x] = h[threadIdx.x];
 }
 
-// thread d owns digit d: running sum over blocks (coalesced rows), block scan of the digit totals
+// thread d owns digit d: running sum over blocks (coalesced rows), block scan of the digit totals.
+// Reads hist, writes offs (distinct buffers, so the loads of several blocks can be in flight at once).
 __global__ void __launch_bounds__(kRadix)
-radix_offsets_kernel(uint32_t *__restrict__ hist, int nblocks) {
+radix_offsets_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ offs, int nblocks) {
     __shared__ uint32_t warp_sums[kRadix / 32];
     const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
     uint32_t total = 0;
+#pragma unroll 8
     for (int b = 0; b < nblocks; ++b) total += hist[(int64_t)b * kRadix + d];
     uint32_t incl = total;
 #pragma unroll
@@ -144,9 +146,10 @@ radix_offsets_kernel(uint32_t *__restrict__ hist, int nblocks) {
     __syncthreads();
     uint32_t base = incl - total;
     for (int w = 0; w < warp; ++w) base += warp_sums[w];
+#pragma unroll 8
     for (int b = 0; b < nblocks; ++b) {
         const uint32_t c = hist[(int64_t)b * kRadix + d];
-        hist[(int64_t)b * kRadix + d] = base;
+        offs[(int64_t)b * kRadix + d] = base;
         base += c;
     }
 }
@@ -208,7 +211,7 @@ static_assert(kSortThreads == kRadix, "one thread per digit in the carry pass");
 
 size_t radix_scratch_bytes(int64_t n) {
     int64_t nblocks = ceil_div(n > 0 ? n : 1, kSortTile);
-    return (size_t)round_up(nblocks * kRadix * 4, 256);
+    return 2 * (size_t)round_up(nblocks * kRadix * 4, 256);
 }
 
 int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
@@ -220,6 +223,7 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_
     }
     const int nblocks = (int)ceil_div(n, kSortTile);
     uint32_t *hist = (uint32_t *)scratch;
+    uint32_t *offs = (uint32_t *)((char *)scratch + round_up((int64_t)nblocks * kRadix * 4, 256));
     uint64_t *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
     for (int lo = bit_lo; lo < bit_hi; lo += kRadixBits) {
@@ -227,9 +231,9 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_
         const uint32_t mask = (1u << bits) - 1u;
         radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, n, lo, mask, hist);
         ORIE_LAUNCH_CHECK();
-        radix_offsets_kernel<<<1, kRadix, 0, st>>>(hist, nblocks);
+        radix_offsets_kernel<<<1, kRadix, 0, st>>>(hist, offs, nblocks);
         ORIE_LAUNCH_CHECK();
-        radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, lo, mask, hist);
+        radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, lo, mask, offs);
         ORIE_LAUNCH_CHECK();
         uint64_t *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;

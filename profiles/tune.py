@@ -16,13 +16,17 @@ dev = torch.device("cuda:0")
 hp = HostPacked(pk)
 dp = DevicePacked(hp, dev)
 torch.cuda.synchronize()
-for sc in segs:
+waves = os.environ.get("TUNE_WAVES", "").split(",") if os.environ.get("TUNE_WAVES") else [None]
+for sc in [(a, w) for a in segs for w in waves]:
+    sc, wv = sc
+    if wv is not None:
+        os.environ["ORIE_WALK_WAVES"] = wv
     eng = Engine(dp, iouv=iouv, seg_chunks=sc)
     rows = []
     for rep in range(6):
         rows.append(eng.profile_reward(N, seed=rep))
     med = {k: float(np.median([r[k] for r in rows[1:]])) for k in rows[0]}
-    print("seg_chunks", sc, eng.info["segments"], {k: round(v, 3) for k, v in med.items()}, flush=True)
+    print("seg_chunks", sc, "waves", wv, eng.info["segments"], {k: round(v, 3) for k, v in med.items()}, flush=True)
     eng.close()
 
 # e2e breakdown
