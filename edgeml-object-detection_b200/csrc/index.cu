@@ -357,12 +357,8 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         ORIE_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
         ORIE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
     }
-    // ---- sizes (three small D2H reads)
-    ORIE_CUDA(cudaMemcpyAsync(&tails[0], w_off + M, 8, cudaMemcpyDeviceToHost, st));
-    ORIE_CUDA(cudaMemcpyAsync(&tails[1], s_off + M, 8, cudaMemcpyDeviceToHost, st));
-    ORIE_CUDA(cudaMemcpyAsync(&tails[2], l_off + M, 8, cudaMemcpyDeviceToHost, st));
-    ORIE_CUDA(cudaStreamSynchronize(st));
-    const int64_t Dw = ix->Dw = tails[0], Ds = ix->Ds = tails[1], G = ix->G = tails[2];
+    // ---- sizes: given by the caller; off[M] of each block is read back with the class counts and cross-checked
+    const int64_t Dw = ix->Dw, Ds = ix->Ds, G = ix->G;
     if (Dw < 0 || Ds < 0 || G < 0 || Dw >= ((int64_t)1 << 27) || Ds >= ((int64_t)1 << 27) || G >= ((int64_t)1 << 31)) {
         set_error("orie_index_build: row counts out of range (weak %lld, strong %lld, labels %lld; limit 2^27-1 detections per detector)",
                   (long long)Dw, (long long)Ds, (long long)G);
@@ -444,7 +440,15 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     // ---- host: class counts -> padded layouts and segment tables
     ORIE_CUDA(cudaMemcpyAsync(h_hist.data(), hist, (size_t)(2 * C) * 4, cudaMemcpyDeviceToHost, st));
     ORIE_CUDA(cudaMemcpyAsync(&h_status, status, 4, cudaMemcpyDeviceToHost, st));
+    ORIE_CUDA(cudaMemcpyAsync(&tails[0], w_off + M, 8, cudaMemcpyDeviceToHost, st));
+    ORIE_CUDA(cudaMemcpyAsync(&tails[1], s_off + M, 8, cudaMemcpyDeviceToHost, st));
+    ORIE_CUDA(cudaMemcpyAsync(&tails[2], l_off + M, 8, cudaMemcpyDeviceToHost, st));
     ORIE_CUDA(cudaStreamSynchronize(st));
+    if (tails[0] != Dw || tails[1] != Ds || tails[2] != G) {
+        set_error("orie_index_build: row counts (%lld, %lld, %lld) do not match the offset arrays (%lld, %lld, %lld)",
+                  (long long)Dw, (long long)Ds, (long long)G, (long long)tails[0], (long long)tails[1], (long long)tails[2]);
+        return ORIE_EDATA;
+    }
     if (h_status & 2) {
         set_error("orie_index_build: class id outside [0, %lld)", (long long)C);
         return ORIE_EDATA;
@@ -581,7 +585,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
 
 using namespace orie;
 
-extern "C" int orie_index_build(int64_t M, int64_t C, int T,
+extern "C" int orie_index_build(int64_t M, int64_t C, int T, int64_t num_weak, int64_t num_strong, int64_t num_labels,
                                 const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                                 const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
                                 const int64_t *l_off, const int32_t *l_cls, int seg_chunks, orie_stream_t stream,
@@ -606,6 +610,7 @@ extern "C" int orie_index_build(int64_t M, int64_t C, int T,
     }
     orie_index *ix = new orie_index();
     ix->M = M; ix->C = C; ix->T = T;
+    ix->Dw = num_weak; ix->Ds = num_strong; ix->G = num_labels;
     ix->stream = stream;
     ix->nbatch = ceil_div(M, 32);
     ix->ens_words = ceil_div(M + 1, 32);

@@ -127,60 +127,90 @@ radix_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint3
     hist[(int64_t)blockIdx.x * kRadix + threadIdx.x] = h[threadIdx.x];
 }
 
-// thread d owns digit d: running sum over blocks (coalesced rows), block scan of the digit totals.
-// Reads hist, writes offs (distinct buffers, so the loads of several blocks can be in flight at once).
-__global__ void __launch_bounds__(kRadix)
-radix_offsets_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ offs, int nblocks) {
-    __shared__ uint32_t warp_sums[kRadix / 32];
-    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
-    uint32_t total = 0;
+// One warp per digit: lane l owns a contiguous run of blocks; exclusive prefix over the blocks of that digit
+// (offs[block][digit]) and the digit's total.  The digit bases (exclusive scan over the 256 totals) are added
+// by the scatter kernel itself.
+constexpr int kOffsetsThreads = 256;
+__global__ void __launch_bounds__(kOffsetsThreads)
+radix_offsets_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ offs, uint32_t *__restrict__ totals,
+                     int nblocks) {
+    const int d = (blockIdx.x * kOffsetsThreads + threadIdx.x) >> 5;
+    if (d >= kRadix) return;
+    const int lane = threadIdx.x & 31;
+    const int per = (nblocks + 31) / 32;
+    const int b0 = lane * per, b1 = min(b0 + per, nblocks);
+    uint32_t sum = 0;
 #pragma unroll 8
-    for (int b = 0; b < nblocks; ++b) total += hist[(int64_t)b * kRadix + d];
-    uint32_t incl = total;
+    for (int b = b0; b < b1; ++b) sum += hist[(int64_t)b * kRadix + d];
+    uint32_t incl = sum;
 #pragma unroll
     for (int k = 1; k < 32; k <<= 1) {
         uint32_t y = __shfl_up_sync(kFull, incl, k);
         if (lane >= k) incl += y;
     }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    uint32_t base = incl - total;
-    for (int w = 0; w < warp; ++w) base += warp_sums[w];
+    uint32_t run = incl - sum;
 #pragma unroll 8
-    for (int b = 0; b < nblocks; ++b) {
+    for (int b = b0; b < b1; ++b) {
         const uint32_t c = hist[(int64_t)b * kRadix + d];
-        offs[(int64_t)b * kRadix + d] = base;
-        base += c;
+        offs[(int64_t)b * kRadix + d] = run;
+        run += c;
     }
+    if (lane == 31) totals[d] = incl;
+}
+
+// lanes holding the same digit as this lane: 9 ballots (8 digit bits + validity) instead of MATCH.ANY,
+// whose latency grows with the number of distinct values in the warp
+__device__ __forceinline__ unsigned digit_peers(int dg, bool ok) {
+    unsigned peers = __ballot_sync(kFull, ok);
+#pragma unroll
+    for (int b = 0; b < kRadixBits; ++b) {
+        const bool bit = (dg >> b) & 1;
+        const unsigned vote = __ballot_sync(kFull, bit);
+        peers &= bit ? vote : ~vote;
+    }
+    return peers;
 }
 
 // Stable scatter.  Warp w of a block owns items [w*512, (w+1)*512) of the tile, walked in 16 steps of 32
-// consecutive items; __match_any_sync ranks equal digits inside a step, per-warp digit counters carry the
-// rank across steps and warps.
+// consecutive items; ballots rank equal digits inside a step, per-warp digit counters carry the rank across
+// steps and warps.
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                      uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
-                     int shift, uint32_t mask, const uint32_t *__restrict__ offs) {
+                     int shift, uint32_t mask, const uint32_t *__restrict__ offs, const uint32_t *__restrict__ totals) {
     __shared__ uint32_t cnt[kSortWarps][kRadix];
+    __shared__ uint32_t wsum[kSortWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
+    // digit base = exclusive scan of the digit totals (thread d owns digit d)
+    const uint32_t my_total = totals[threadIdx.x];
+    uint32_t incl = my_total;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+        uint32_t y = __shfl_up_sync(kFull, incl, k);
+        if (lane >= k) incl += y;
+    }
+    if (lane == 31) wsum[warp] = incl;
     __syncthreads();
+    uint32_t digit_base = incl - my_total;
+    for (int w = 0; w < warp; ++w) digit_base += wsum[w];
     const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * (32 * kSortSteps);
     uint64_t k[kSortSteps];
+    unsigned peers[kSortSteps];
 #pragma unroll
     for (int s = 0; s < kSortSteps; ++s) {
         const int64_t i = wbase + s * 32 + lane;
         const bool ok = i < n;
         k[s] = ok ? keys[i] : 0ull;
-        const int dg = ok ? digit_of(k[s], shift, mask) : kRadix;
-        const unsigned peers = __match_any_sync(kFull, dg);
-        if (ok && lane == (__ffs(peers) - 1)) cnt[warp][dg] += __popc(peers);
+        const int dg = digit_of(k[s], shift, mask);
+        peers[s] = digit_peers(dg, ok);
+        if (ok && lane == (__ffs(peers[s]) - 1)) cnt[warp][dg] += __popc(peers[s]);
         __syncwarp();
     }
     __syncthreads();
     {
         const int d = threadIdx.x;  // kSortThreads == kRadix
-        uint32_t run = offs[(int64_t)blockIdx.x * kRadix + d];
+        uint32_t run = offs[(int64_t)blockIdx.x * kRadix + d] + digit_base;
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
             const uint32_t c = cnt[w][d];
@@ -193,15 +223,14 @@ radix_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restri
     for (int s = 0; s < kSortSteps; ++s) {
         const int64_t i = wbase + s * 32 + lane;
         const bool ok = i < n;
-        const int dg = ok ? digit_of(k[s], shift, mask) : kRadix;
-        const unsigned peers = __match_any_sync(kFull, dg);
+        const int dg = digit_of(k[s], shift, mask);
         uint32_t pos = 0;
-        if (ok) pos = cnt[warp][dg] + __popc(peers & ((1u << lane) - 1u));
+        if (ok) pos = cnt[warp][dg] + __popc(peers[s] & ((1u << lane) - 1u));
         __syncwarp();
         if (ok) {
             keys_out[pos] = k[s];
             vals_out[pos] = vals[i];
-            if (lane == (__ffs(peers) - 1)) cnt[warp][dg] += __popc(peers);
+            if (lane == (__ffs(peers[s]) - 1)) cnt[warp][dg] += __popc(peers[s]);
         }
         __syncwarp();
     }
@@ -211,7 +240,7 @@ static_assert(kSortThreads == kRadix, "one thread per digit in the carry pass");
 
 size_t radix_scratch_bytes(int64_t n) {
     int64_t nblocks = ceil_div(n > 0 ? n : 1, kSortTile);
-    return 2 * (size_t)round_up(nblocks * kRadix * 4, 256);
+    return 2 * (size_t)round_up(nblocks * kRadix * 4, 256) + kRadix * 4;
 }
 
 int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
@@ -224,6 +253,7 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_
     const int nblocks = (int)ceil_div(n, kSortTile);
     uint32_t *hist = (uint32_t *)scratch;
     uint32_t *offs = (uint32_t *)((char *)scratch + round_up((int64_t)nblocks * kRadix * 4, 256));
+    uint32_t *totals = (uint32_t *)((char *)scratch + 2 * round_up((int64_t)nblocks * kRadix * 4, 256));
     uint64_t *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
     for (int lo = bit_lo; lo < bit_hi; lo += kRadixBits) {
@@ -231,9 +261,9 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_
         const uint32_t mask = (1u << bits) - 1u;
         radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, n, lo, mask, hist);
         ORIE_LAUNCH_CHECK();
-        radix_offsets_kernel<<<1, kRadix, 0, st>>>(hist, offs, nblocks);
+        radix_offsets_kernel<<<kRadix * 32 / kOffsetsThreads, kOffsetsThreads, 0, st>>>(hist, offs, totals, nblocks);
         ORIE_LAUNCH_CHECK();
-        radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, lo, mask, offs);
+        radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, lo, mask, offs, totals);
         ORIE_LAUNCH_CHECK();
         uint64_t *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;

@@ -121,7 +121,7 @@ class Engine:
     def _build_index(self, seg_chunks):
         h = C.c_void_p(0)
         _lib.check(self.lib.orie_index_build(
-            self.M, self.Cn, self.T, _ptr(self.w_off), _ptr(self.w_cls), _ptr(self.w_conf), _ptr(self.w_tp),
+            self.M, self.Cn, self.T, self.Dw, self.Ds, self.G, _ptr(self.w_off), _ptr(self.w_cls), _ptr(self.w_conf), _ptr(self.w_tp),
             _ptr(self.s_off), _ptr(self.s_cls), _ptr(self.s_conf), _ptr(self.s_tp), _ptr(self.l_off), _ptr(self.l_cls),
             int(seg_chunks), self._s(), C.byref(h)))
         self._handle = h

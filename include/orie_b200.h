@@ -102,6 +102,7 @@ typedef struct {
 } orie_index_info_t;
 
 int orie_index_build(int64_t M, int64_t C, int T,
+                     int64_t num_weak, int64_t num_strong, int64_t num_labels, /* == off[M] of each block */
                      const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                      const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
                      const int64_t *l_off, const int32_t *l_cls,
