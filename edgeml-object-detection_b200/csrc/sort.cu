@@ -105,7 +105,7 @@ constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortSteps = 16;                      // 32-item steps per warp
+constexpr int kSortSteps = 8;                       // 32-item steps per warp
 constexpr int kSortTile = kSortThreads * kSortSteps;  // 4096 items per block
 
 __device__ __forceinline__ int digit_of(uint64_t key, int shift, uint32_t mask) {
@@ -171,7 +171,7 @@ __device__ __forceinline__ unsigned digit_peers(int dg, bool ok) {
     return peers;
 }
 
-// Stable scatter.  Warp w of a block owns items [w*512, (w+1)*512) of the tile, walked in 16 steps of 32
+// Stable scatter.  Warp w of a block owns items [w*32*kSortSteps, (w+1)*32*kSortSteps) of the tile, walked in kSortSteps steps of 32
 // consecutive items; ballots rank equal digits inside a step, per-warp digit counters carry the rank across
 // steps and warps.
 __global__ void __launch_bounds__(kSortThreads)
