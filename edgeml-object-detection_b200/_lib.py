@@ -66,7 +66,7 @@ def load():
     lib.orie_dcsb.restype = C.c_int
     lib.orie_dcsb.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     lib.orie_index_build.restype = C.c_int
-    lib.orie_index_build.argtypes = [i64, i64, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, C.POINTER(vp)]
+    lib.orie_index_build.argtypes = [i64, i64, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, C.POINTER(vp)]
     lib.orie_index_destroy.restype = None
     lib.orie_index_destroy.argtypes = [vp]
     lib.orie_index_info.restype = C.c_int

@@ -338,7 +338,7 @@ static int upload(Builder &B, Tp **dst, const std::vector<Tp> &src, bool keep) {
 
 static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                  const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
-                 const int64_t *l_off, const int32_t *l_cls, int seg_chunks_req, cudaStream_t st) {
+                 const int64_t *l_off, const int32_t *l_cls, int seg_chunks_req, cudaEvent_t tp_ready, cudaStream_t st) {
     // host staging buffers are declared before the Builder so that they outlive its destructor, which
     // synchronises the stream (asynchronous copies from / into them may still be in flight on error paths)
     const int64_t M = ix->M, C = ix->C;
@@ -500,6 +500,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     fill_u32_kernel<<<grid_for(ix->P), 256, 0, st>>>(ix->slot_img, ix->P, (uint32_t)M);
     ORIE_LAUNCH_CHECK();
     ORIE_CUDA(cudaMemsetAsync(slot_tp, 0, (size_t)ix->P * 2, st));
+    if (tp_ready) ORIE_CUDA(cudaStreamWaitEvent(st, tp_ready, 0));     // first reader of the true-positive masks
     if (n) {
         place_slots_kernel<<<grid_for(n), 256, 0, st>>>(dets, order, wpre, img_all, n, d_cls_off, d_pad_off, ix->slot_img,
                                                       slot_tp, q_of_det);
@@ -588,8 +589,8 @@ using namespace orie;
 extern "C" int orie_index_build(int64_t M, int64_t C, int T, int64_t num_weak, int64_t num_strong, int64_t num_labels,
                                 const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                                 const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
-                                const int64_t *l_off, const int32_t *l_cls, int seg_chunks, orie_stream_t stream,
-                                orie_index_t **out) {
+                                const int64_t *l_off, const int32_t *l_cls, int seg_chunks, orie_event_t tp_ready,
+                                orie_stream_t stream, orie_index_t **out) {
     if (!out) {
         set_error("orie_index_build: out is NULL");
         return ORIE_EINVAL;
@@ -616,7 +617,7 @@ extern "C" int orie_index_build(int64_t M, int64_t C, int T, int64_t num_weak, i
     ix->ens_words = ceil_div(M + 1, 32);
     ix->cls_per_warp = 32 / T;
     ix->class_groups = ceil_div(C, ix->cls_per_warp);
-    int rc = build(ix, w_off, w_cls, w_conf, w_tp, s_off, s_cls, s_conf, s_tp, l_off, l_cls, seg_chunks, stream);
+    int rc = build(ix, w_off, w_cls, w_conf, w_tp, s_off, s_cls, s_conf, s_tp, l_off, l_cls, seg_chunks, tp_ready, stream);
     if (rc != ORIE_OK) {
         orie_index_destroy(ix);
         return rc;

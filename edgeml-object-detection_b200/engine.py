@@ -44,6 +44,17 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_SIDE = {}
+
+
+def _side_streams(device):
+    """(copy stream, matcher stream) of a device, created once."""
+    key = (device.type, device.index)
+    if key not in _SIDE:
+        _SIDE[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _SIDE[key]
+
+
 _FIELDS = ("w_off", "w_box", "w_conf", "w_cls", "s_off", "s_box", "s_conf", "s_cls", "l_off", "l_box", "l_cls")
 
 
@@ -90,21 +101,62 @@ class Engine:
         with torch.cuda.device(self.device):
             self.stream = stream or torch.cuda.current_stream()
             with torch.cuda.stream(self.stream):
-                d = packed if isinstance(packed, DevicePacked) else DevicePacked(packed, self.device)
-                self.h2d_bytes = d.nbytes
-                for k in _FIELDS:
-                    setattr(self, k, getattr(d, k))
-                self.Dw, self.Ds, self.G = int(self.w_cls.numel()), int(self.s_cls.numel()), int(self.l_cls.numel())
-                self._match()
-                self._build_index(seg_chunks)
+                if isinstance(packed, DevicePacked):
+                    self._adopt(packed)
+                    self._match(self.stream)
+                    self._build_index(seg_chunks, None)
+                else:
+                    self._pipelined_setup(packed if isinstance(packed, HostPacked) else HostPacked(packed), seg_chunks)
+
+    def _adopt(self, d):
+        self.h2d_bytes = d.nbytes
+        for k in _FIELDS:
+            setattr(self, k, getattr(d, k))
+        self.Dw, self.Ds, self.G = int(self.w_cls.numel()), int(self.s_cls.numel()), int(self.l_cls.numel())
+
+    def _pipelined_setup(self, hp, seg_chunks):
+        """Host -> HBM with the copies overlapped with compute: the small arrays (offsets, classes,
+        confidences; all the index sort needs) go first, the boxes (70 % of the bytes, needed only by
+        the matcher) follow on the copy stream while the sort already runs; the matcher runs on a side
+        stream and the index build waits for its event only where it first reads the TP masks."""
+        dev, main = self.device, self.stream
+        copy_s, match_s = _side_streams(dev)
+        copy_s.wait_stream(main)
+        small = [k for k in _FIELDS if not k.endswith("_box")]
+        boxes = [k for k in _FIELDS if k.endswith("_box")]
+        ev_small, ev_boxes, ev_tp = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        with torch.cuda.stream(copy_s):
+            for k in small:
+                setattr(self, k, getattr(hp, k).to(dev, non_blocking=True))
+            ev_small.record(copy_s)
+            for k in boxes:
+                setattr(self, k, getattr(hp, k).to(dev, non_blocking=True))
+            ev_boxes.record(copy_s)
+        for k in _FIELDS:
+            t = getattr(self, k)
+            t.record_stream(main)
+            t.record_stream(match_s)
+        self.h2d_bytes = hp.nbytes
+        self.Dw, self.Ds, self.G = int(self.w_cls.numel()), int(self.s_cls.numel()), int(self.l_cls.numel())
+        main.wait_event(ev_small)
+        match_s.wait_stream(main)
+        match_s.wait_event(ev_boxes)
+        with torch.cuda.stream(match_s):
+            self._match(match_s)
+            ev_tp.record(match_s)
+        for t in (self.w_tp, self.w_match, self.w_biou, self.s_tp, self.s_match, self.s_biou):
+            t.record_stream(main)
+        self._build_index(seg_chunks, ev_tp)
+        main.wait_event(ev_tp)
 
     # ------------------------------------------------------------------ setup
 
     def _s(self):
         return C.c_void_p(self.stream.cuda_stream)
 
-    def _match(self):
+    def _match(self, on_stream):
         dev = self.device
+        st = C.c_void_p(on_stream.cuda_stream)
         iou_p = self.iouv.ctypes.data_as(C.POINTER(C.c_double))
 
         def run(box, cls, off, n):
@@ -112,18 +164,19 @@ class Engine:
             mi = torch.full((max(n, 1),), -1, dtype=torch.int32, device=dev)
             bi = torch.zeros(max(n, 1), dtype=torch.float64, device=dev)
             _lib.check(self.lib.orie_match(_ptr(box), _ptr(cls), _ptr(off), _ptr(self.l_box), _ptr(self.l_cls),
-                                           _ptr(self.l_off), iou_p, self.T, self.M, _ptr(tp), _ptr(mi), _ptr(bi), self._s()))
+                                           _ptr(self.l_off), iou_p, self.T, self.M, _ptr(tp), _ptr(mi), _ptr(bi), st))
             return tp, mi, bi
 
         self.w_tp, self.w_match, self.w_biou = run(self.w_box, self.w_cls, self.w_off, self.Dw)
         self.s_tp, self.s_match, self.s_biou = run(self.s_box, self.s_cls, self.s_off, self.Ds)
 
-    def _build_index(self, seg_chunks):
+    def _build_index(self, seg_chunks, tp_ready):
         h = C.c_void_p(0)
+        ev = C.c_void_p(tp_ready.cuda_event) if tp_ready is not None else C.c_void_p(0)
         _lib.check(self.lib.orie_index_build(
             self.M, self.Cn, self.T, self.Dw, self.Ds, self.G, _ptr(self.w_off), _ptr(self.w_cls), _ptr(self.w_conf), _ptr(self.w_tp),
             _ptr(self.s_off), _ptr(self.s_cls), _ptr(self.s_conf), _ptr(self.s_tp), _ptr(self.l_off), _ptr(self.l_cls),
-            int(seg_chunks), self._s(), C.byref(h)))
+            int(seg_chunks), ev, self._s(), C.byref(h)))
         self._handle = h
         info = _lib.IndexInfo()
         _lib.check(self.lib.orie_index_info(h, C.byref(info)))

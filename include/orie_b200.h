@@ -40,6 +40,7 @@ extern "C" {
 #endif
 
 typedef struct CUstream_st *orie_stream_t; /* == cudaStream_t */
+typedef struct CUevent_st *orie_event_t;   /* == cudaEvent_t */
 
 enum {
     ORIE_OK = 0,
@@ -87,6 +88,9 @@ int orie_dcsb(const double *w_conf, const int64_t *w_off, const double *s_conf, 
  * per-image own-detection lists and the class-sorted label stream.  It is the
  * target-independent part of what reward.py:40-49 + lib/metrics.py:100-104
  * recompute for every target (gather + argsort + unique).
+ * tp_ready (nullable): an event recorded after w_tp / s_tp were produced (e.g. by orie_match on another
+ * stream).  The build sorts by (class, confidence) first and only waits for the event where it first reads
+ * the true-positive masks, so matching — and the host-to-device copy of the boxes it needs — overlaps the sort.
  */
 typedef struct orie_index orie_index_t;
 
@@ -106,7 +110,8 @@ int orie_index_build(int64_t M, int64_t C, int T,
                      const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                      const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
                      const int64_t *l_off, const int32_t *l_cls,
-                     int seg_chunks /* 0 = auto */, orie_stream_t stream, orie_index_t **out);
+                     int seg_chunks /* 0 = auto */, orie_event_t tp_ready /* nullable */,
+                     orie_stream_t stream, orie_index_t **out);
 void orie_index_destroy(orie_index_t *idx);
 int orie_index_info(const orie_index_t *idx, orie_index_info_t *info);
 
