@@ -21,6 +21,8 @@
 // (explicit _rn intrinsics; the library is built with -fmad=false).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "index.cuh"
 
 namespace orie {
@@ -139,6 +141,7 @@ struct WalkParams {
     int64_t M, nt, ntp, t0;
     int64_t ens_words;
     const uint32_t *ens_bits;   // [nt][ens_words]
+    uint32_t *memb_global;      // [ntp / 32][ens_words * 32] membership tables in global memory (GMEM kernels)
     // stream
     const uint32_t *slot_img;
     const int32_t *seg_chunk0, *seg_nch;
@@ -158,27 +161,44 @@ struct WalkParams {
 };
 
 
+// Membership table of one batch in global memory, for datasets whose table exceeds shared memory
+// (more than ~58 k images): memb_global[batch][img] bit j = img in the ensemble of target 32*batch+j.
+__global__ void membership_table_kernel(const WalkParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t lb = blockIdx.x, tl = lb * 32 + lane;
+    Transposer transpose;
+    transpose.init(lane);
+    const uint32_t *row = p.ens_bits + tl * p.ens_words;
+    const bool live = tl < p.nt;
+    uint32_t *out = p.memb_global + lb * p.ens_words * 32;
+    for (int64_t w = (int64_t)blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); w < p.ens_words;
+         w += (int64_t)gridDim.y * (blockDim.x >> 5))
+        out[w * 32 + lane] = transpose(live ? row[w] : 0u);
+}
+
 // THREADS is the block size the kernel is launched with (256 / 512 / 1024, chosen from the size of the
-// membership table); the register cap keeps 1536+ threads resident per SM.
-template <bool DETS, int THREADS>
+// membership table); the register cap keeps 1536+ threads resident per SM.  GMEM: the membership table was
+// built by membership_table_kernel and is read through L1 instead of shared memory.
+template <bool DETS, int THREADS, bool GMEM>
 __global__ void __launch_bounds__(THREADS, 1536 / THREADS > 0 ? 1536 / THREADS : 1)
 walk_kernel(const WalkParams p) {
-    extern __shared__ uint32_t memb[];   // [ens_words * 32]: bit j of memb[img] = img in ensemble of target 32*batch+j
+    extern __shared__ uint32_t memb_s[];   // [ens_words * 32]: bit j of memb[img] = img in ensemble of target 32*batch+j
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kWarps = blockDim.x >> 5;
     const int64_t lb = blockIdx.x;                 // local batch
     const int64_t tl = lb * 32 + lane;             // local target of this lane
     Transposer transpose;
     transpose.init(lane);
-    {
+    const uint32_t *memb = GMEM ? p.memb_global + lb * p.ens_words * 32 : memb_s;
+    if (!GMEM) {
         const uint32_t *row = p.ens_bits + tl * p.ens_words;
         const bool live = tl < p.nt;
         for (int64_t w = warp; w < p.ens_words; w += kWarps) {
             const uint32_t x = live ? row[w] : 0u;
-            memb[w * 32 + lane] = transpose(x);
+            memb_s[w * 32 + lane] = transpose(x);
         }
+        __syncthreads();
     }
-    __syncthreads();
     const int64_t gb = (p.t0 >> 5) + lb;           // global batch (query lists are per global batch)
     const int64_t sbeg = (int64_t)blockIdx.y * p.segs_per_block;
     const int64_t send = min(sbeg + p.segs_per_block, p.S);
@@ -211,7 +231,7 @@ walk_kernel(const WalkParams p) {
                 eb = __shfl_sync(kFull, ebv, c & 31);
                 if (lane < __popc(eb)) mymask = p.evmask[ev_i + lane];   // this chunk's event masks, one per lane
             }
-            const uint32_t word = transpose(memb[img]);   // bit l: slot l holds a member of MY target
+            const uint32_t word = transpose(GMEM ? __ldg(memb + img) : memb[img]);   // bit l: slot l holds a member of MY target
             if (DETS) {
                 int e = 0;
                 while (eb) {
@@ -499,7 +519,7 @@ __global__ void finalize_kernel(const double *__restrict__ partial, int64_t nt, 
 // workspace
 // ----------------------------------------------------------------------------
 struct WsLayout {
-    size_t tot, evcnt, totL, ev, cb_w, cb_s, partial, total;
+    size_t tot, evcnt, totL, ev, cb_w, cb_s, partial, memb, total;
 };
 
 static WsLayout ws_layout(const orie_index *ix, int64_t nt) {
@@ -514,6 +534,8 @@ static WsLayout ws_layout(const orie_index *ix, int64_t nt) {
     L.cb_w = take(ix->Dw * 4);
     L.cb_s = take(ix->Ds * 4);
     L.partial = take(ntp * ix->class_groups * 3 * 8);
+    // membership tables in global memory, only when they exceed shared memory (or when forced for tests)
+    L.memb = take(((size_t)ix->ens_words * 32 * 4 > 227 * 1024 || getenv("ORIE_WALK_GMEM")) ? (ntp / 32) * ix->ens_words * 32 * 4 : 0);
     L.total = o;
     return L;
 }
@@ -575,17 +597,19 @@ extern "C" int orie_ensemble_sample(const orie_index_t *ix, int64_t t0, int64_t 
     return ORIE_OK;
 }
 
-template <bool DETS, int THREADS>
+template <bool DETS, int THREADS, bool GMEM>
 static int launch_walk_t(dim3 grid, size_t smem, cudaStream_t stream, const WalkParams &p) {
-    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<DETS, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    walk_kernel<DETS, THREADS><<<grid, THREADS, smem, stream>>>(p);
+    if (!GMEM)
+        ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<DETS, THREADS, GMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    walk_kernel<DETS, THREADS, GMEM><<<grid, THREADS, GMEM ? 0 : smem, stream>>>(p);
     return ORIE_OK;
 }
 template <bool DETS>
-static int launch_walk(dim3 grid, int threads, size_t smem, cudaStream_t stream, const WalkParams &p) {
-    if (threads == 256) return launch_walk_t<DETS, 256>(grid, smem, stream, p);
-    if (threads == 512) return launch_walk_t<DETS, 512>(grid, smem, stream, p);
-    return launch_walk_t<DETS, 1024>(grid, smem, stream, p);
+static int launch_walk(dim3 grid, int threads, size_t smem, bool gmem, cudaStream_t stream, const WalkParams &p) {
+    if (gmem) return launch_walk_t<DETS, 256, true>(grid, smem, stream, p);
+    if (threads == 256) return launch_walk_t<DETS, 256, false>(grid, smem, stream, p);
+    if (threads == 512) return launch_walk_t<DETS, 512, false>(grid, smem, stream, p);
+    return launch_walk_t<DETS, 1024, false>(grid, smem, stream, p);
 }
 
 static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
@@ -609,11 +633,8 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     char *ws = (char *)workspace;
     const int64_t ntp = round_up(nt, 32);
     const size_t smem = (size_t)ix->ens_words * 32 * 4;
-    if (smem > 227 * 1024) {
-        set_error("orie_reward: %lld images need %zu bytes of shared memory for the membership table (limit %d)",
-                  (long long)ix->M, smem, 227 * 1024);
-        return ORIE_ELIMIT;
-    }
+    const char *force_gmem = getenv("ORIE_WALK_GMEM");               // developer / test knob
+    const bool gmem = smem > 227 * 1024 || (force_gmem && atoi(force_gmem) != 0);
     static_assert(sizeof(WalkParams) < 4000 && sizeof(ApParams) + sizeof(Grid101) < 4000, "kernel parameter space");
 
     WalkParams wp;
@@ -621,7 +642,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     wp.M = ix->M; wp.nt = nt; wp.ntp = ntp; wp.t0 = t0;
     wp.ens_words = ix->ens_words; wp.ens_bits = ens_bits;
     const int64_t nb = ntp / 32;
-    const int walk_threads = smem <= 56 * 1024 ? 256 : smem <= 112 * 1024 ? 512 : 1024;   // keep the SM full of warps
+    const int walk_threads = gmem ? 256 : smem <= 56 * 1024 ? 256 : smem <= 112 * 1024 ? 512 : 1024;   // keep the SM full of warps
     auto segs_per_block = [&](int64_t S) {
         // enough blocks for two full waves of resident blocks (2048 threads per SM) when the data allows,
         // at least one segment per warp
@@ -635,6 +656,12 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         return (int)spb;
     };
     if (marks) ORIE_CUDA(cudaEventRecord(marks[0], stream));
+    if (gmem) {
+        wp.memb_global = (uint32_t *)(ws + L.memb);
+        dim3 grid((unsigned)nb, (unsigned)std::min<int64_t>(ceil_div(ix->ens_words, 8), 64));
+        membership_table_kernel<<<grid, 256, 0, stream>>>(wp);
+        ORIE_LAUNCH_CHECK();
+    }
     // labels
     if (ix->SL > 0) {
         WalkParams lp = wp;
@@ -642,7 +669,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         lp.S = ix->SL; lp.segs_per_block = segs_per_block(ix->SL);
         lp.tot = (uint32_t *)(ws + L.totL);
         dim3 grid((unsigned)nb, (unsigned)ceil_div(ix->SL, lp.segs_per_block));
-        ORIE_TRY(launch_walk<false>(grid, walk_threads, smem, stream, lp));
+        ORIE_TRY(launch_walk<false>(grid, walk_threads, smem, gmem, stream, lp));
         ORIE_LAUNCH_CHECK();
     }
     if (marks) ORIE_CUDA(cudaEventRecord(marks[1], stream));
@@ -659,7 +686,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         wp.cb_w = (uint32_t *)(ws + L.cb_w);
         wp.cb_s = (uint32_t *)(ws + L.cb_s);
         dim3 grid((unsigned)nb, (unsigned)ceil_div(ix->S, wp.segs_per_block));
-        ORIE_TRY(launch_walk<true>(grid, walk_threads, smem, stream, wp));
+        ORIE_TRY(launch_walk<true>(grid, walk_threads, smem, gmem, stream, wp));
         ORIE_LAUNCH_CHECK();
     }
     if (marks) ORIE_CUDA(cudaEventRecord(marks[2], stream));

@@ -141,6 +141,8 @@ int orie_ensemble_sample(const orie_index_t *idx, int64_t t0, int64_t nt, int64_
  * Replaces reward.py:16-52 (compute_orie) + :86 (NaN -> 0) and, inside it,
  * lib/metrics.py:89-124 (ap_per_class) + :127-148 (compute_ap).  N is the
  * (already clamped) ensemble size used for the (N+1) multiplier; N = 0 is ORI.
+ * Datasets whose 32-target membership table ((M+1) * 4 bytes) exceeds shared memory keep it in the workspace
+ * and read it through L1 (slower walk, no limit on M below 2^27).
  * detail (nullable): f64[nt,3] = (sum of weak APs, sum of strong APs, number
  * of ground-truth classes) per target, for parity checks.
  */

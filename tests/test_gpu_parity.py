@@ -108,3 +108,19 @@ def test_bad_ensemble_is_reported():
     with pytest.raises(OrieError):
         eng.orie(N, ens_matrix=em)
     eng.close()
+
+
+def test_global_memory_membership_table_matches(monkeypatch):
+    """Datasets beyond ~58 k images keep the 32-target membership table in global memory instead of shared
+    memory; force that path on a small dataset and demand identical bits."""
+    M, N = 130, 50
+    _, pk = make_packed(M=M, seed=44)
+    eng = _engine(pk, O.IOU_05_095)
+    em = O.ensemble_matrix(M, N, 9)
+    ref = eng.orie(N, ens_matrix=em)
+    monkeypatch.setenv("ORIE_WALK_GMEM", "1")
+    eng2 = _engine(pk, O.IOU_05_095)
+    got = eng2.orie(N, ens_matrix=em)
+    monkeypatch.delenv("ORIE_WALK_GMEM")
+    assert np.array_equal(ref, got)
+    eng.close(); eng2.close()
