@@ -64,5 +64,32 @@ def main():
         print(path, os.path.getsize(path), "bytes")
 
 
+def main_testmap():
+    """Fixture for the realised-mAP sweep (upstream test.py): dataset + CV split + two estimate sets -> test_map."""
+    M, K = 48, 3
+    ds = synth.make("smoke500", num_images=M, seed=31, empty_det_frac=0.05)
+    rng = np.random.default_rng(5)
+    fold = rng.permutation(M) % K
+    split = np.stack([fold == k for k in range(K)])
+    out = dict(l_off=ds.labels.off, l_rows=ds.labels.rows, w_off=ds.weak.off, w_rows=ds.weak.rows,
+               s_off=ds.strong.off, s_rows=ds.strong.rows, split=split)
+    with tempfile.TemporaryDirectory() as d:
+        w, s, l = synth.write_dirs(ds, d)
+        est_dirs = []
+        for e in range(2):
+            ed = os.path.join(d, f"est{e}")
+            os.makedirs(ed)
+            for k in range(K):
+                tr, va = rng.normal(size=int((~split[k]).sum())), rng.normal(size=int(split[k].sum()))
+                np.savez(os.path.join(ed, f"estimate{k + 1}.npz"), train_est=tr, val_est=va)
+                out[f"est{e}_train{k + 1}"], out[f"est{e}_val{k + 1}"] = tr, va
+            est_dirs.append(ed)
+        out["test_map"] = R.ref_test_map(w, s, l, est_dirs, split)
+    path = os.path.join(OUT, "coco48_testmap.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes", out["test_map"].shape)
+
+
 if __name__ == "__main__":
     main()
+    main_testmap()

@@ -118,3 +118,18 @@ def ref_ap_per_class(tp, conf, pred_cls, target_cls):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         return metrics.ap_per_class(tp, conf, pred_cls, target_cls)
+
+
+def ref_test_map(weak_dir, strong_dir, label_dir, estimate_dirs, dataset_split):
+    """Upstream test.py:test_map on upstream's own set_data cache (T = 1, as shipped)."""
+    import importlib.util
+    with _ref_path():
+        spec = importlib.util.spec_from_file_location("_upstream_test", os.path.join(REF_ROOT, "test.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    _, _, data = modules()
+    weak_data, strong_data, labels = data.set_data(weak_dir, strong_dir, label_dir)
+    labels = np.concatenate(labels).astype(int)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return mod.test_map(weak_data, strong_data, labels, list(estimate_dirs), dataset_split)

@@ -14,7 +14,7 @@ from orie_b200.synth import Rows
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not p.endswith("_testmap.npz"))
 
 
 def _engine(pk, iouv, **kw):
@@ -185,3 +185,31 @@ def test_full_size_coco_shape_properties():
     eng = _engine(data.pack(ds.labels, ds.weak, ds.weak), O.IOU_05_095)
     assert (eng.orie(N, seed=1) == 0).all()
     eng.close()
+
+
+def test_realised_map_sweep_matches_frozen_reference(tmp_path):
+    """The reference's test.py (realised mAP vs offloading ratio) through the engine and through the CLI drop-in."""
+    from orie_b200 import evaluate
+    from test_oracle_golden import _testmap_case
+    z, lab, wk, st, masks = _testmap_case(tmp_path)
+    got = evaluate.realised_map(lab, wk, st, masks, iouv=O.IOU_05)
+    assert np.abs(got.reshape(2, 11) - z["test_map"]).max() < 1e-9
+    # every image weak / every image strong == plain dataset mAP of each detector
+    pk = data.pack(lab, wk, st)
+    wd, sd, lc = oracle_cache(pk, O.IOU_05_095)
+    gt = np.concatenate(lc).astype(int)
+    both = evaluate.realised_map(lab, wk, st, np.stack([np.zeros(48, bool), np.ones(48, bool)]), iouv=O.IOU_05_095)
+    for cache, val in ((wd, both[0]), (sd, both[1])):
+        cols = [np.concatenate(c, axis=0) for c in zip(*cache)]
+        assert abs(np.mean(O.ap_by_class(*cols, gt)) - val) < 1e-9
+    # CLI
+    ds_dir = tmp_path / "ds"
+    from orie_b200.synth import SynthDataset
+    names = [f"{i:012d}" for i in range(lab.num_images)]
+    w, s, l = synth.write_dirs(SynthDataset(names, lab, wk, st, 80), str(ds_dir))
+    np.save(tmp_path / "split.npy", z["split"])
+    out = tmp_path / "out"
+    subprocess.run([sys.executable, os.path.join(ROOT, "test.py"), w, s, l, str(tmp_path / "split.npy"), str(out),
+                    "--estimates", str(tmp_path / "est0"), str(tmp_path / "est1")], check=True, capture_output=True,
+                   timeout=300, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert np.abs(np.load(out / "test_map.npy") - z["test_map"]).max() < 1e-9

@@ -10,7 +10,7 @@ from helpers import O, flat_tp, oracle_cache
 from orie_b200 import data
 from orie_b200.synth import Rows
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not p.endswith("_testmap.npz"))
 
 
 def load_case(path):
@@ -72,3 +72,36 @@ def test_known_answers_from_survey():
     wd = [(np.zeros((1, 1), bool), np.array([0.9]), np.array([0]))]
     out = O.orie_all(wd, wd, [np.array([])], np.zeros((1, 0), dtype=np.int32))
     assert out[0] == 0
+
+
+def _testmap_case(tmp_path):
+    from orie_b200 import evaluate
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "coco48_testmap.npz"))
+    lab, wk, st = Rows(z["l_off"], z["l_rows"]), Rows(z["w_off"], z["w_rows"]), Rows(z["s_off"], z["s_rows"])
+    split = z["split"]
+    dirs = []
+    for e in range(2):
+        d = tmp_path / f"est{e}"
+        d.mkdir()
+        for k in range(split.shape[0]):
+            np.savez(d / f"estimate{k + 1}.npz", train_est=z[f"est{e}_train{k + 1}"], val_est=z[f"est{e}_val{k + 1}"])
+        dirs.append(str(d))
+    masks = np.concatenate([evaluate.offload_masks_from_estimates(d, split) for d in dirs], axis=0)
+    return z, lab, wk, st, masks
+
+
+def test_offload_policy_and_oracle_reproduce_frozen_test_map(tmp_path):
+    """test.py:26-42 — the threshold policy (host code of the product) and the oracle's dataset-wide AP against the
+    test_map the live reference produced."""
+    z, lab, wk, st, masks = _testmap_case(tmp_path)
+    assert masks.shape == (22, lab.num_images)
+    assert not masks[0].any() or masks[0].sum() < masks[10].sum()
+    pk = data.pack(lab, wk, st)
+    wd, sd, lc = oracle_cache(pk, O.IOU_05)
+    gt = np.concatenate(lc).astype(int)
+    got = []
+    for m in masks:
+        recs = [sd[i] if m[i] else wd[i] for i in range(len(m))]
+        cols = [np.concatenate(c, axis=0) for c in zip(*recs)]
+        got.append(np.mean(O.ap_by_class(*cols, gt)))
+    assert np.abs(np.array(got).reshape(2, 11) - z["test_map"]).max() < 1e-12
