@@ -535,7 +535,7 @@ static WsLayout ws_layout(const orie_index *ix, int64_t nt) {
     L.cb_s = take(ix->Ds * 4);
     L.partial = take(ntp * ix->class_groups * 3 * 8);
     // membership tables in global memory, only when they exceed shared memory (or when forced for tests)
-    L.memb = take(((size_t)ix->ens_words * 32 * 4 > 227 * 1024 || getenv("ORIE_WALK_GMEM")) ? (ntp / 32) * ix->ens_words * 32 * 4 : 0);
+    L.memb = take(((size_t)ix->ens_words * 32 * 4 > 112 * 1024 || getenv("ORIE_WALK_GMEM")) ? (ntp / 32) * ix->ens_words * 32 * 4 : 0);
     L.total = o;
     return L;
 }
@@ -634,7 +634,9 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     const int64_t ntp = round_up(nt, 32);
     const size_t smem = (size_t)ix->ens_words * 32 * 4;
     const char *force_gmem = getenv("ORIE_WALK_GMEM");               // developer / test knob
-    const bool gmem = smem > 227 * 1024 || (force_gmem && atoi(force_gmem) != 0);
+    // beyond 112 KB a shared-memory table would allow only one 1024-thread block per SM; the L1/L2-served global
+    // table with six 256-thread blocks per SM is measurably faster there (profiles/: 157 vs 168 ms at M = 50 000)
+    const bool gmem = smem > 112 * 1024 || (force_gmem && atoi(force_gmem) != 0);
     static_assert(sizeof(WalkParams) < 4000 && sizeof(ApParams) + sizeof(Grid101) < 4000, "kernel parameter space");
 
     WalkParams wp;
@@ -642,7 +644,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     wp.M = ix->M; wp.nt = nt; wp.ntp = ntp; wp.t0 = t0;
     wp.ens_words = ix->ens_words; wp.ens_bits = ens_bits;
     const int64_t nb = ntp / 32;
-    const int walk_threads = gmem ? 256 : smem <= 56 * 1024 ? 256 : smem <= 112 * 1024 ? 512 : 1024;   // keep the SM full of warps
+    const int walk_threads = gmem ? 256 : smem <= 56 * 1024 ? 256 : 512;   // keep the SM full of warps
     auto segs_per_block = [&](int64_t S) {
         // enough blocks for two full waves of resident blocks (2048 threads per SM) when the data allows,
         // at least one segment per warp
