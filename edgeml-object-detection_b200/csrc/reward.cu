@@ -393,6 +393,15 @@ struct OwnCursor {
 
 constexpr int kApThreads = 128;
 
+// FULL = false (normal operation): only the DIFFERENCE of the two variants' integrals is needed, so
+//  * a class in which the target has no detection from either detector is skipped (identical integrals);
+//  * the sweep of a (class, threshold) stops as soon as the variants can no longer differ: once every own
+//    detection lies behind (lower confidence), both variants see the same ranks, the same count of remaining true
+//    positives and the same grid pointer; from then on they take the max with the same ratios, so when their
+//    envelope values meet they stay equal and every later (higher-confidence) term cancels exactly.
+//    The sums written are then partial (common part omitted in both).
+// FULL = true (detail requested): both integrals are completed, the sums are the true AP sums.
+template <bool FULL>
 __global__ void __launch_bounds__(kApThreads, 8)
 ap_kernel(const ApParams p, const Grid101 grid) {
     __shared__ double cw[102];
@@ -441,6 +450,7 @@ ap_kernel(const ApParams p, const Grid101 grid) {
             // the target has no detection of this class from either detector: both variants are the same integral
             const bool same = (wb == wa) && (sb == sa);
             if (same) vs.dead = true;
+            if (same && !FULL) vw.dead = true;
             if (!(vw.dead && vs.dead)) {
                 OwnCursor ow, os;
                 ow.init(wq, wcb, wm, wa, wb, t);
@@ -451,6 +461,7 @@ ap_kernel(const ApParams p, const Grid101 grid) {
                 uint32_t base = n_ens, slot0 = 0;
                 const uint64_t *e = ev;
                 for (;;) {
+                    if (!FULL && !ow.valid && !os.valid && vw.E == vs.E && vw.k == vs.k && vw.g == vs.g) break;
                     if (i < 0) {
                         if (s < s1) {                       // leaving a segment: its remaining own detections
                             ow.drain(vw, cw, ge, base, slot0, 0u, t);
@@ -727,7 +738,8 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
                          grid101.ge[3] == 0x1fu) ? 1u : 0u;
     }
     const int64_t items = nt * ix->class_groups;
-    ap_kernel<<<(unsigned)ceil_div(items, kApThreads / 32), kApThreads, 0, stream>>>(ap, grid101);
+    if (detail) ap_kernel<true><<<(unsigned)ceil_div(items, kApThreads / 32), kApThreads, 0, stream>>>(ap, grid101);
+    else ap_kernel<false><<<(unsigned)ceil_div(items, kApThreads / 32), kApThreads, 0, stream>>>(ap, grid101);
     ORIE_LAUNCH_CHECK();
     if (marks) ORIE_CUDA(cudaEventRecord(marks[3], stream));
     finalize_kernel<<<(unsigned)ceil_div(nt, 128), 128, 0, stream>>>(ap.partial, nt, ix->class_groups, ix->T, N, reward, detail);
