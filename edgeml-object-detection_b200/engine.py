@@ -102,9 +102,18 @@ class Engine:
             self.stream = stream or torch.cuda.current_stream()
             with torch.cuda.stream(self.stream):
                 if isinstance(packed, DevicePacked):
+                    # matching runs on a side stream while the index build sorts by (class, confidence)
                     self._adopt(packed)
-                    self._match(self.stream)
-                    self._build_index(seg_chunks, None)
+                    _, match_s = _side_streams(self.device)
+                    match_s.wait_stream(self.stream)
+                    ev_tp = torch.cuda.Event()
+                    with torch.cuda.stream(match_s):
+                        self._match(match_s)
+                        ev_tp.record(match_s)
+                    for t in (self.w_tp, self.w_match, self.w_biou, self.s_tp, self.s_match, self.s_biou):
+                        t.record_stream(self.stream)
+                    self._build_index(seg_chunks, ev_tp)
+                    self.stream.wait_event(ev_tp)
                 else:
                     self._pipelined_setup(packed if isinstance(packed, HostPacked) else HostPacked(packed), seg_chunks)
 
