@@ -342,14 +342,36 @@ def run_b200(args):
     alg_bytes = float(per_target[t0:t0 + nt].sum())          # bytes one launch on this rank accounts for
     means = {k: (sum(v) / len(v) if v else 0.0) for k, v in kernel_ms.items()}
     dom = max(("walk_ms", "ap_ms"), key=lambda k: means[k])
+
+    def profiled_traffic(kernel_prefix):
+        """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed `ncu --set full` capture of
+        this same command (profiles/r01_ncu_raw_selected.csv), per launch; None if there is no capture."""
+        import csv
+        path = os.path.join(ROOT, "profiles", "r01_ncu_raw_selected.csv")
+        if not os.path.exists(path) or args.workload != "coco5000" or world != 1:
+            return None
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if kernel_prefix in r[0]:
+                tot = 0.0
+                for col in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    i = hdr.index(col)
+                    tot += float(r[i]) * scale.get(units[i], 1.0)
+                return tot
+        return None
     achieved = alg_bytes / (means[dom] / 1e3) / 1e9 if means[dom] > 0 else 0.0
     reward_phase_ms = sum(means.values())
     roofline = {"bound": "hbm", "kernel": {"walk_ms": "walk_kernel<true>", "ap_ms": "ap_kernel"}[dom],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profiled_traffic({"walk_ms": "walk_kernel<1", "ap_ms": "ap_kernel"}[dom]),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": means,
                 "reward_phase": {"ms": reward_phase_ms, "achieved": alg_bytes / (reward_phase_ms / 1e3) / 1e9 if reward_phase_ms else 0.0},
-                "note": "working set is L2-resident; algorithmic bytes are the records upstream gathers per target (SURVEY §8d)"}
+                "note": "algorithmic bytes = the records upstream gathers per target (SURVEY 8d); the engine never moves them "
+                        "(dataset and index are L2-resident, ensembles are membership tests, the AP sweep stops when the two "
+                        "variants can no longer differ), so frac can exceed 1 - see DESIGN.md section 4 and the ncu traffic"}
 
     # ---- CPU baseline (rank 0, one thread, bounded sample) + live parity check on that sample
     cpu = None

@@ -236,6 +236,85 @@ def ap_reverse(ix, c, t, tot, events, own, n_l):
     return v.ap
 
 
+def delta_reverse(ix, c, t, tot, events, own_w, own_s, n_l):
+    """AP_strong - AP_weak of class c at threshold bit t, the way ap_kernel<false> computes it: both variants are
+    swept together and the sweep stops once they can no longer differ (all own detections behind, equal envelope,
+    equal remaining-TP count and grid pointer) — every later term is identical in both and cancels."""
+    if len(own_w[0]) == 0 and len(own_s[0]) == 0:
+        return 0.0, 0
+    s0, s1 = ix.cls_seg0[c], ix.cls_seg0[c + 1]
+    n_ens = int(tot[s0:s1].sum())
+    K_ens = sum(1 for s in range(s0, s1) for (_, m) in events[s] if (m >> t) & 1)
+    var, cur = [], []
+    for q, mk, cb in (own_w, own_s):
+        var.append(_Var(K_ens + sum(1 for m in mk if (m >> t) & 1), n_ens + len(q), n_l))
+        cur.append(len(q) - 1)
+    owns = (own_w, own_s)
+    steps = 0
+
+    def drain(v, base, slot0, limit):
+        q, mk, cb = owns[v]
+        while cur[v] >= 0 and q[cur[v]] >= slot0 and base + cb[cur[v]] >= limit:
+            if (mk[cur[v]] >> t) & 1:
+                var[v].step(base + int(cb[cur[v]]) + 1 + cur[v])
+            cur[v] -= 1
+
+    def converged():
+        a, b = var
+        return cur[0] < 0 and cur[1] < 0 and a.E == b.E and a.k == b.k and a.g == b.g
+
+    if not (var[0].dead and var[1].dead):
+        rem, done = n_ens, False
+        for s in range(s1 - 1, s0 - 1, -1):
+            rem -= int(tot[s])
+            base, slot0 = rem, ix.seg_chunk0[s] * CHUNK
+            for (p_rel, m) in reversed(events[s]):
+                if converged():
+                    done = True
+                    break
+                p = base + p_rel
+                drain(0, base, slot0, p)
+                drain(1, base, slot0, p)
+                if (m >> t) & 1:
+                    var[0].step(p + cur[0] + 1)
+                    var[1].step(p + cur[1] + 1)
+                    steps += 1
+            if done:
+                break
+            drain(0, base, slot0, 0)
+            drain(1, base, slot0, 0)
+    aw = 0.0 if var[0].dead else var[0].ap
+    as_ = 0.0 if var[1].dead else var[1].ap
+    return as_ - aw, steps
+
+
+def reward_target_delta(ix: Index, j: int, ens_idx, T: int):
+    """reward_target via delta_reverse (difference-only sweep); also returns the number of TP steps taken."""
+    M, C = ix.M, ix.C
+    member = np.zeros(M + 1, dtype=bool)
+    member[np.asarray(ens_idx, dtype=np.int64)] = True
+    tot, events, cb_w, cb_s = walk_target(ix, member, j)
+    n_l_all = ix.gtcnt[member[:M]].sum(axis=0) + ix.gtcnt[j]
+    sl = lambda a, off: a[off[j]:off[j + 1]]
+    wc, sc = sl(ix.own_w_c, ix.off_w), sl(ix.own_s_c, ix.off_s)
+    wq, sq = sl(ix.own_w_q, ix.off_w), sl(ix.own_s_q, ix.off_s)
+    wm, sm = sl(ix.own_w_m, ix.off_w), sl(ix.own_s_m, ix.off_s)
+    delta, nc, steps = 0.0, 0, 0
+    for c in range(C):
+        n_l = int(n_l_all[c])
+        if n_l == 0:
+            continue
+        nc += 1
+        a, b = wc == c, sc == c
+        for t in range(T):
+            d, st = delta_reverse(ix, c, t, tot, events, (wq[a], wm[a], cb_w[a]), (sq[b], sm[b], cb_s[b]), n_l)
+            delta += d
+            steps += st
+    if nc == 0:
+        return 0.0, 0
+    return delta / (nc * T) * (len(ens_idx) + 1), steps
+
+
 def reward_target(ix: Index, j: int, ens_idx, T: int):
     M, C = ix.M, ix.C
     member = np.zeros(M + 1, dtype=bool)

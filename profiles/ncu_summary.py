@@ -14,7 +14,7 @@ for r in rows[2:]:
                 except: v=r[idx[w]]
                 if isinstance(v,float) and 'stalled' in w and v<0.15: continue
                 print(f"  {w.replace('smsp__average_warps_issue_stalled_','stall_').replace('_per_issue_active.ratio','')} = {r[idx[w]]} {units[idx[w]]}")
-src=subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass','--kernel-name','regex:'+kern.replace('<','.').replace('>','.')],capture_output=True,text=True).stdout
+src=subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass','--kernel-name','regex:'+kern.replace('<','.').replace('>','.').replace('<','.').replace('>','.')],capture_output=True,text=True).stdout
 rows=list(csv.reader(src.splitlines()))
 h=[i for i,r in enumerate(rows) if r and r[0]=='Line No'][0]
 hdr=rows[h]; ci=hdr.index('Instructions Executed'); si=hdr.index('# Samples'); ti=hdr.index('Thread Instructions Executed')

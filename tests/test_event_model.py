@@ -24,6 +24,9 @@ def test_event_model_equals_oracle(M, N, T, segch, seed):
     want = O.orie_all(wd, sd, lc, em)
     got = np.array([E.reward_target(ix, j, em[j], T) for j in range(M)])
     assert np.abs(got - want).max() < 1e-9
+    # difference-only sweep with early exit (what ap_kernel<false> does): same rewards, far fewer steps
+    delta = [E.reward_target_delta(ix, j, em[j], T) for j in range(M)]
+    assert np.abs(np.array([d[0] for d in delta]) - want).max() < 1e-9
 
 
 def test_integer_recall_rule_equals_float_comparison():
