@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=32, help="targets in the single-thread CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seg-chunks", type=int, default=0, help="segment length override (0 = engine default)")
+    ap.add_argument("--shard", default="classes", choices=["classes", "targets"],
+                    help="multi-GPU decomposition: classes (whole pipeline shrinks per rank, one all-reduce of 3 doubles "
+                         "per target) or targets (index replicated, one all-gather of reward slices)")
     ap.add_argument("--workspace-gb", type=int, default=16, help="reward-pass workspace budget; targets run in waves that fit")
     return ap.parse_args()
 
@@ -209,7 +212,7 @@ def run_b200(args):
     import torch.distributed as dist
     import orie_b200  # noqa: F401
     from orie_b200 import _lib
-    from orie_b200.engine import DevicePacked, Engine, HostPacked, shard_range
+    from orie_b200.engine import DevicePacked, Engine, HostPacked, class_shard, rewards_from_sums, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -225,12 +228,16 @@ def run_b200(args):
 
     ds, pk, N, iouv = dataset(args.workload, args.num_images)
     M, T = pk.num_images, len(iouv)
+    by_class = world > 1 and args.shard == "classes"
+    pk_all = pk
+    if by_class:
+        pk = class_shard(pk_all, rank, world)        # this rank's classes, all images (host-side partition, untimed)
     hp = HostPacked(pk)                      # pinned once, outside every timed region
     dp = DevicePacked(hp, dev)               # resident in HBM for the `value` steps
-    t0, nt = shard_range(M, rank, world)
-    per = shard_range(M, 0, world)[1]
+    t0, nt = (0, M) if by_class else shard_range(M, rank, world)
+    per = M if by_class else shard_range(M, 0, world)[1]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    gathered = torch.empty(per * world, dtype=torch.float64, device=dev)
+    gathered = torch.empty(M if by_class else per * world, dtype=torch.float64, device=dev)
 
     def barrier():
         if world > 1:
@@ -250,6 +257,7 @@ def run_b200(args):
         ws = eng._workspace(eng.workspace_bytes(wave))
         bits = torch.empty((max(wave, 1), eng.info["ens_words"]), dtype=torch.int32, device=dev)
         mine = torch.zeros(per, dtype=torch.float64, device=dev)
+        sums = torch.zeros((M, 3), dtype=torch.float64, device=dev) if by_class else None
         import ctypes as C
         s = C.c_void_p(eng.stream.cuda_stream)
         ms = [0.0] * 4
@@ -258,11 +266,15 @@ def run_b200(args):
             cnt = min(wave, nt - a)
             part = (C.c_float * 4)()
             _lib.check(lib.orie_ensemble_sample(eng._handle, t0 + a, cnt, Nc, seed, C.c_void_p(bits.data_ptr()), s))
+            out_r = C.c_void_p(0) if by_class else C.c_void_p(mine.data_ptr() + 8 * a)
+            out_s = C.c_void_p(sums.data_ptr() + 24 * a) if by_class else C.c_void_p(0)
             _lib.check(lib.orie_reward_profile(eng._handle, t0 + a, cnt, C.c_void_p(bits.data_ptr()), Nc,
-                                               C.c_void_p(ws.data_ptr()), ws.numel(),
-                                               C.c_void_p(mine.data_ptr() + 8 * a), C.c_void_p(0), s, part))
+                                               C.c_void_p(ws.data_ptr()), ws.numel(), out_r, out_s, 0, s, part))
             ms = [x + float(y) for x, y in zip(ms, part)]
-        if world > 1:
+        if by_class:
+            dist.all_reduce(sums)                       # 3 doubles per target: AP sums are additive over classes
+            gathered[:M].copy_(rewards_from_sums(sums, T, Nc))
+        elif world > 1:
             dist.all_gather_into_tensor(gathered, mine)
         else:
             gathered.copy_(mine)
@@ -308,14 +320,20 @@ def run_b200(args):
         barrier()
         t_start = time.perf_counter()
         eng = Engine(hp, iouv=iouv, device=dev)
-        mine = torch.zeros(per, dtype=torch.float64, device=dev)
-        if nt > 0:
-            mine[:nt] = eng.orie_device(N, seed=3000 + k, t0=t0, nt=nt)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, mine)
-            host = gathered[:M].cpu()
+        if by_class:
+            sums = eng.orie_sums_device(N, seed=3000 + k, total_images=M).clone()
+            eng.stream.synchronize()
+            dist.all_reduce(sums)
+            host = rewards_from_sums(sums, T, min(N, M - 1)).cpu()
         else:
-            host = mine[:M].cpu()
+            mine = torch.zeros(per, dtype=torch.float64, device=dev)
+            if nt > 0:
+                mine[:nt] = eng.orie_device(N, seed=3000 + k, t0=t0, nt=nt)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, mine)
+                host = gathered[:M].cpu()
+            else:
+                host = mine[:M].cpu()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t_start
         eng.close()
@@ -338,7 +356,7 @@ def run_b200(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    per_target = algorithmic_bytes(pk, N)
+    per_target = algorithmic_bytes(pk, min(N, M - 1))      # pk = this rank's share of the records when classes are sharded
     alg_bytes = float(per_target[t0:t0 + nt].sum())          # bytes one launch on this rank accounts for
     means = {k: (sum(v) / len(v) if v else 0.0) for k, v in kernel_ms.items()}
     dom = max(("walk_ms", "ap_ms"), key=lambda k: means[k])
@@ -376,7 +394,7 @@ def run_b200(args):
     # ---- CPU baseline (rank 0, one thread, bounded sample) + live parity check on that sample
     cpu = None
     parity = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # contract: CPU baseline on rank 0 at N = 1 only
         from oracle import orie_oracle as O
         eng = Engine(dp, iouv=iouv)
         wtp, stp, _, _ = eng.tp_flags()
@@ -400,15 +418,17 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "images": M, "classes": pk.num_classes, "num_ensemble": min(N, M - 1),
-                   "iou_thresholds": T, "weak_dets": int(len(pk.w_cls)), "strong_dets": int(len(pk.s_cls)),
-                   "labels": int(len(pk.l_cls)), "parallelism": f"targets sharded over {world} gpu(s), index replicated",
+        "config": {"workload": args.workload, "images": M, "classes": pk_all.num_classes, "num_ensemble": min(N, M - 1),
+                   "iou_thresholds": T, "weak_dets": int(len(pk_all.w_cls)), "strong_dets": int(len(pk_all.s_cls)),
+                   "labels": int(len(pk_all.l_cls)), "parallelism": (f"classes sharded over {world} gpus (every rank: all targets, its classes), one all-reduce of 3 doubles "
+                                   f"per target" if by_class else f"targets sharded over {world} gpu(s), index replicated, one all-gather"),
                    "step": "TP matching (2 detectors) + index build + ensemble draw + membership walk + AP + all-gather",
                    "l2": "flushed between steps (256 MiB write, not timed)", "ensembles": "device-side Philox draw, seed per step",
                    "index": {k: info[k] for k in ("slots", "segments", "events", "seg_chunks", "class_groups")},
                    "phase_ms": {k: sum(v) / len(v) for k, v in phase_ms.items()}, "wall_s_timed_region": wall},
         "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pk.nbytes()), "d2h_bytes_per_step": int(M * 8),
+                "note": "bytes per rank" if world > 1 else "",
                 "ms_per_step": 1e3 * sum(e2e_times) / len(e2e_times), "timer": "wall clock around Engine(pinned host) + orie + .cpu()"},
         "roofline": roofline, "cpu_baseline": cpu, "parity_max_abs_err_vs_oracle": parity,
     }

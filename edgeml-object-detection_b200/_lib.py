@@ -17,7 +17,7 @@ SYMBOLS = [
     "orie_last_error", "orie_version", "orie_match", "orie_dcsb",
     "orie_index_build", "orie_index_destroy", "orie_index_info",
     "orie_ensemble_from_indices", "orie_ensemble_sample",
-    "orie_reward_workspace_bytes", "orie_reward", "orie_reward_profile", "orie_launch_count",
+    "orie_reward_workspace_bytes", "orie_reward", "orie_reward_sums", "orie_reward_profile", "orie_launch_count",
 ]
 
 
@@ -80,7 +80,9 @@ def load():
     lib.orie_reward.restype = C.c_int
     lib.orie_reward.argtypes = [vp, i64, i64, vp, i64, vp, C.c_size_t, vp, vp, vp]
     lib.orie_reward_profile.restype = C.c_int
-    lib.orie_reward_profile.argtypes = [vp, i64, i64, vp, i64, vp, C.c_size_t, vp, vp, vp, C.POINTER(C.c_float)]
+    lib.orie_reward_sums.restype = C.c_int
+    lib.orie_reward_sums.argtypes = [vp, i64, i64, vp, i64, vp, C.c_size_t, vp, i32, vp]
+    lib.orie_reward_profile.argtypes = [vp, i64, i64, vp, i64, vp, C.c_size_t, vp, vp, i32, vp, C.POINTER(C.c_float)]
     lib.orie_launch_count.restype = C.c_longlong
     lib.orie_launch_count.argtypes = []
     _LIB = lib

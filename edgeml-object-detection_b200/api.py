@@ -15,7 +15,7 @@ from pathlib import Path
 import numpy as np
 
 from . import data
-from .engine import IOU_05, IOU_05_095, Engine, clamp_ensemble, shard_range
+from .engine import IOU_05, IOU_05_095, Engine, class_shard, clamp_ensemble, rewards_from_sums, shard_range
 
 
 def parse_iou_thresholds(spec) -> np.ndarray:
@@ -86,8 +86,8 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
     reference's own timer covers (the reward phase, reward.py:76-88) — here the
     index build, the ensemble draw and the reward kernels; loading and TP
     matching are reported separately in ``info`` like upstream's ``set_data``.
-    Under torchrun (WORLD_SIZE > 1) targets are sharded over the ranks and the
-    slices are combined with one NCCL all-gather."""
+    Under torchrun (WORLD_SIZE > 1) the classes are sharded over the ranks and the
+    per-target AP sums are combined with one NCCL all-reduce."""
     import torch
     method = method.lower()
     if method == "ori":
@@ -123,9 +123,11 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
         dist.broadcast(s, 0)
         seed = int(s.item())
     t = time.perf_counter()
-    # the same dense remap applies on every rank, so results agree across ranks
+    # Multi-GPU: every rank keeps all images and its share of the classes (AP sums are additive over classes), runs
+    # the whole pipeline for all targets and one all-reduce of 3 doubles per target combines the ranks.
     from .engine import HostPacked
-    eng = Engine(HostPacked(pk), iouv=iouv, device=device)
+    by_class = dist is not None and method == "orie"
+    eng = Engine(HostPacked(class_shard(pk, rank, world) if by_class else pk), iouv=iouv, device=device)
     torch.cuda.synchronize()
     t_match = time.perf_counter() - t
     try:
@@ -133,19 +135,14 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
         if method == "dcsb":
             reward = eng.dcsb().astype(int)
         else:
-            t0, nt = shard_range(M, rank, world)
-            em = ensemble_matrix_numpy(M, N, seed, t0, nt) if ensembles == "numpy" else None
-            mine = eng.orie_device(N, ens_matrix=em, seed=seed, t0=t0, nt=nt)
-            if dist is not None:
-                per = shard_range(M, 0, world)[1]
-                pad = torch.zeros(per, dtype=torch.float64, device=eng.device)
-                pad[:nt] = mine
-                out = torch.empty(per * world, dtype=torch.float64, device=eng.device)
+            em = ensemble_matrix_numpy(M, N, seed) if ensembles == "numpy" else None
+            if by_class:
+                sums = eng.orie_sums_device(N, ens_matrix=em, seed=seed, total_images=M).clone()
                 eng.stream.synchronize()
-                dist.all_gather_into_tensor(out, pad)
-                reward = out[:M].cpu().numpy()
+                dist.all_reduce(sums)
+                reward = rewards_from_sums(sums, eng.T, clamp_ensemble(M, N)).cpu().numpy()
             else:
-                reward = mine.cpu().numpy()
+                reward = eng.orie_device(N, ens_matrix=em, seed=seed).cpu().numpy()
             eng.check_status()
             reward = np.where(np.isnan(reward), 0, reward)     # reward.py:86 (the kernel already stores 0)
         seconds = time.perf_counter() - start

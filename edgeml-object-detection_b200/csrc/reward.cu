@@ -522,7 +522,7 @@ __global__ void finalize_kernel(const double *__restrict__ partial, int64_t nt, 
         const double cnt = nc * (double)T;
         r = __dmul_rn(__dsub_rn(__ddiv_rn(ss, cnt), __ddiv_rn(sw, cnt)), (double)(N + 1));
     }
-    reward[tl] = r;   // nc == 0: upstream's mean over an empty AP table is NaN, stored as 0 (reward.py:86)
+    if (reward) reward[tl] = r;   // nc == 0: upstream's mean over an empty AP table is NaN, stored as 0 (reward.py:86)
     if (detail) { detail[tl * 3] = sw; detail[tl * 3 + 1] = ss; detail[tl * 3 + 2] = nc; }
 }
 
@@ -624,10 +624,10 @@ static int launch_walk(dim3 grid, int threads, size_t smem, bool gmem, cudaStrea
 }
 
 static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
-                      void *workspace, size_t workspace_bytes, double *reward, double *detail, cudaStream_t stream,
-                      cudaEvent_t *marks /* 5 events or NULL */) {
+                      void *workspace, size_t workspace_bytes, double *reward, double *detail, bool full,
+                      cudaStream_t stream, cudaEvent_t *marks /* 5 events or NULL */) {
     ORIE_TRY(check_range(ix, t0, nt, "orie_reward"));
-    if (!ens_bits || !reward || !workspace || N < 0) {
+    if (!ens_bits || (!reward && !detail) || !workspace || N < 0) {
         set_error("orie_reward: null buffer or negative N");
         return ORIE_EINVAL;
     }
@@ -738,7 +738,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
                          grid101.ge[3] == 0x1fu) ? 1u : 0u;
     }
     const int64_t items = nt * ix->class_groups;
-    if (detail) ap_kernel<true><<<(unsigned)ceil_div(items, kApThreads / 32), kApThreads, 0, stream>>>(ap, grid101);
+    if (full) ap_kernel<true><<<(unsigned)ceil_div(items, kApThreads / 32), kApThreads, 0, stream>>>(ap, grid101);
     else ap_kernel<false><<<(unsigned)ceil_div(items, kApThreads / 32), kApThreads, 0, stream>>>(ap, grid101);
     ORIE_LAUNCH_CHECK();
     if (marks) ORIE_CUDA(cudaEventRecord(marks[3], stream));
@@ -750,11 +750,20 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
 
 extern "C" int orie_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
                            void *workspace, size_t workspace_bytes, double *reward, double *detail, orie_stream_t stream) {
-    return run_reward(ix, t0, nt, ens_bits, N, workspace, workspace_bytes, reward, detail, stream, nullptr);
+    return run_reward(ix, t0, nt, ens_bits, N, workspace, workspace_bytes, reward, detail, detail != nullptr, stream, nullptr);
+}
+
+extern "C" int orie_reward_sums(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
+                                void *workspace, size_t workspace_bytes, double *sums, int full, orie_stream_t stream) {
+    if (!sums) {
+        set_error("orie_reward_sums: sums is NULL");
+        return ORIE_EINVAL;
+    }
+    return run_reward(ix, t0, nt, ens_bits, N, workspace, workspace_bytes, nullptr, sums, full != 0, stream, nullptr);
 }
 
 extern "C" int orie_reward_profile(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
-                                   void *workspace, size_t workspace_bytes, double *reward, double *detail,
+                                   void *workspace, size_t workspace_bytes, double *reward, double *detail, int full,
                                    orie_stream_t stream, float *kernel_ms_host) {
     if (!kernel_ms_host) {
         set_error("orie_reward_profile: kernel_ms_host is NULL");
@@ -762,7 +771,7 @@ extern "C" int orie_reward_profile(const orie_index_t *ix, int64_t t0, int64_t n
     }
     cudaEvent_t marks[5];
     for (int i = 0; i < 5; ++i) ORIE_CUDA(cudaEventCreate(&marks[i]));
-    int rc = run_reward(ix, t0, nt, ens_bits, N, workspace, workspace_bytes, reward, detail, stream, marks);
+    int rc = run_reward(ix, t0, nt, ens_bits, N, workspace, workspace_bytes, reward, detail, full != 0, stream, marks);
     if (rc == ORIE_OK && nt > 0) {
         cudaError_t e = cudaEventSynchronize(marks[4]);
         if (e != cudaSuccess) {

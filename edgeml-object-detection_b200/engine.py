@@ -44,6 +44,55 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def class_partition(packed: Packed, world: int):
+    """Assign every class to one of ``world`` ranks, balancing the detection + label rows (largest first,
+    always to the lightest rank).  Returns int32[C] rank of each class."""
+    C_ = packed.num_classes
+    load = (np.bincount(packed.w_cls, minlength=C_) + np.bincount(packed.s_cls, minlength=C_)
+            + np.bincount(packed.l_cls, minlength=C_)).astype(np.int64)
+    owner = np.zeros(C_, dtype=np.int32)
+    weight = np.zeros(world, dtype=np.int64)
+    for c in np.argsort(-load, kind="stable"):
+        r = int(np.argmin(weight))
+        owner[c] = r
+        weight[r] += load[c] + 1
+    return owner
+
+
+def class_shard(packed: Packed, rank: int, world: int) -> Packed:
+    """The rows of ``packed`` whose class belongs to ``rank`` — every image is kept (ensembles are drawn over images),
+    classes are re-numbered densely.  AP sums are additive over classes, so the per-target sums of the shards add up to
+    the sums of the whole dataset."""
+    owner = class_partition(packed, world)
+    mine = np.nonzero(owner == rank)[0]
+    remap = np.full(packed.num_classes, -1, dtype=np.int32)
+    remap[mine] = np.arange(len(mine), dtype=np.int32)
+    M = packed.num_images
+
+    def take(off, cls, *cols):
+        keep = remap[cls] >= 0
+        img = np.repeat(np.arange(M), np.diff(off))
+        cnt = np.bincount(img[keep], minlength=M)
+        noff = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        return (noff, remap[cls[keep]].astype(np.int32)) + tuple(np.ascontiguousarray(c[keep]) for c in cols)
+
+    w_off, w_cls, w_box, w_conf = take(packed.w_off, packed.w_cls, packed.w_box, packed.w_conf)
+    s_off, s_cls, s_box, s_conf = take(packed.s_off, packed.s_cls, packed.s_box, packed.s_conf)
+    l_off, l_cls, l_box = take(packed.l_off, packed.l_cls, packed.l_box)
+    return Packed(num_images=M, num_classes=max(len(mine), 1), class_values=packed.class_values[mine],
+                  w_off=w_off, w_box=w_box, w_conf=w_conf, w_cls=w_cls, s_off=s_off, s_box=s_box, s_conf=s_conf, s_cls=s_cls,
+                  l_off=l_off, l_box=l_box, l_cls=l_cls)
+
+
+def rewards_from_sums(sums, T: int, n_used: int):
+    """(mean strong AP - mean weak AP) * (N + 1) from per-target sums (torch or numpy), NaN -> 0 (reward.py:50,86)."""
+    sw, ss, nc = sums[:, 0], sums[:, 1], sums[:, 2]
+    cnt = nc * T
+    safe = cnt.clamp(min=1) if torch.is_tensor(cnt) else np.maximum(cnt, 1)
+    r = (ss / safe - sw / safe) * (n_used + 1)
+    return r * (nc > 0)
+
+
 _SIDE = {}
 
 
@@ -305,8 +354,42 @@ class Engine:
             _lib.check(self.lib.orie_ensemble_sample(self._handle, t0, nt, N, int(seed) & (2**64 - 1), _ptr(bits), self._s()))
             ms = (C.c_float * 4)()
             _lib.check(self.lib.orie_reward_profile(self._handle, t0, nt, _ptr(bits), N, _ptr(ws), ws.numel(),
-                                                    _ptr(reward), C.c_void_p(0), self._s(), ms))
+                                                    _ptr(reward), C.c_void_p(0), 0, self._s(), ms))
         return dict(label_walk_ms=ms[0], walk_ms=ms[1], ap_ms=ms[2], finalize_ms=ms[3])
+
+    def orie_sums_device(self, num_ensemble: int, ens_matrix=None, seed: int = 0, t0: int = 0, nt=None,
+                         workspace_budget: int = 8 << 30, full: bool = False, total_images=None):
+        """f64[nt, 3] device tensor (sum of weak APs, sum of strong APs, classes with ground truth) per target.
+        ``full=False``: only the difference of the two sums is meaningful.  ``total_images``: ensemble-size clamp
+        of the un-sharded dataset (class-sharded runs)."""
+        nt = self.M - t0 if nt is None else int(nt)
+        N = clamp_ensemble(self.M if total_images is None else total_images, num_ensemble)
+        dev = self.device
+        sums = torch.zeros((max(nt, 1), 3), dtype=torch.float64, device=dev)
+        if nt == 0:
+            return sums[:0]
+        with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            if ens_matrix is not None:
+                em = ens_matrix if torch.is_tensor(ens_matrix) else torch.from_numpy(np.ascontiguousarray(ens_matrix, dtype=np.int32))
+                if em.device != dev:
+                    em = (em.pin_memory() if em.numel() else em).to(dev, non_blocking=True)
+                em = em.to(torch.int32).contiguous()
+            wave = self.wave_size(nt, workspace_budget)
+            ws = self._workspace(self.workspace_bytes(wave))
+            bits = torch.empty((wave, self.info["ens_words"]), dtype=torch.int32, device=dev)
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+            for a in range(0, nt, wave):
+                n = min(wave, nt - a)
+                if ens_matrix is not None:
+                    _lib.check(self.lib.orie_ensemble_from_indices(self._handle, t0 + a, n, _ptr(em[a:a + n]), N,
+                                                                   _ptr(bits), _ptr(status), self._s()))
+                else:
+                    _lib.check(self.lib.orie_ensemble_sample(self._handle, t0 + a, n, N, int(seed) & (2**64 - 1),
+                                                             _ptr(bits), self._s()))
+                _lib.check(self.lib.orie_reward_sums(self._handle, t0 + a, n, _ptr(bits), N, _ptr(ws), ws.numel(),
+                                                     _ptr(sums[a:]), 1 if full else 0, self._s()))
+            self._status = status
+        return sums[:nt]
 
     def check_status(self):
         st = int(self._status.item()) if self._status is not None else 0
@@ -325,25 +408,42 @@ class Engine:
 
 
 def compute_rewards(packed: Packed, method: str = "orie", num_ensemble: int = 1000, iouv=IOU_05, ens_matrix=None,
-                    seed: int = 0, device=None, distributed: bool = False):
-    """Reward vector of the whole dataset (what ``reward.py:main`` computes
-    between its two timers, plus ``set_data``'s matching).  With
-    ``distributed=True`` (under torchrun, NCCL) every rank computes its target
-    shard and the slices are combined with one all-gather."""
+                    seed: int = 0, device=None, distributed: bool = False, shard: str = "classes"):
+    """Reward vector of the whole dataset (what ``reward.py:main`` computes between its two timers, plus
+    ``set_data``'s matching).  With ``distributed=True`` (under torchrun, NCCL) the work is split over the ranks:
+
+    * ``shard="classes"`` (default): every rank keeps all images but only the detections / labels of its share of
+      the classes, runs the whole pipeline on that shard for ALL targets, and the per-target AP sums (3 doubles per
+      target) are combined with one all-reduce.  Matching, the index build, the walk and the AP sweep all shrink
+      with the rank count.
+    * ``shard="targets"``: every rank holds the whole dataset and computes a contiguous block of targets; the
+      reward slices are combined with one all-gather (the index build is replicated)."""
     method = method.lower()
     if method == "ori":
         method, num_ensemble = "orie", 0
+    if method not in ("orie", "dcsb"):
+        raise ValueError(f"unknown method {method!r}")
+    M = int(packed.num_images)
+    if not distributed or method == "dcsb":
+        eng = Engine(packed, iouv=iouv, device=device)
+        try:
+            return eng.dcsb() if method == "dcsb" else eng.orie(num_ensemble, ens_matrix=ens_matrix, seed=seed)
+        finally:
+            eng.close()
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if shard == "classes":
+        eng = Engine(class_shard(packed, rank, world), iouv=iouv, device=device)
+        try:
+            sums = eng.orie_sums_device(num_ensemble, ens_matrix=ens_matrix, seed=seed, total_images=M).clone()
+            eng.stream.synchronize()
+            dist.all_reduce(sums)
+            eng.check_status()
+            return rewards_from_sums(sums, eng.T, clamp_ensemble(M, num_ensemble)).cpu().numpy()
+        finally:
+            eng.close()
     eng = Engine(packed, iouv=iouv, device=device)
     try:
-        if method == "dcsb":
-            return eng.dcsb()
-        if method != "orie":
-            raise ValueError(f"unknown method {method!r}")
-        M = eng.M
-        if not distributed:
-            return eng.orie(num_ensemble, ens_matrix=ens_matrix, seed=seed)
-        import torch.distributed as dist
-        rank, world = dist.get_rank(), dist.get_world_size()
         t0, nt = shard_range(M, rank, world)
         sub = None if ens_matrix is None else ens_matrix[t0:t0 + nt]
         mine = eng.orie_device(num_ensemble, ens_matrix=sub, seed=seed, t0=t0, nt=nt)

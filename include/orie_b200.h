@@ -151,12 +151,22 @@ int orie_reward(const orie_index_t *idx, int64_t t0, int64_t nt, const uint32_t 
                 void *workspace, size_t workspace_bytes, double *reward, double *detail, orie_stream_t stream);
 
 /*
- * Same as orie_reward, with CUDA events recorded on `stream` around each kernel; synchronises and
+ * Per-target sums instead of rewards: sums f64[nt,3] = (sum of weak APs, sum of strong APs, number of ground-truth
+ * classes).  full = 0: only the DIFFERENCE sums[.,1] - sums[.,0] is meaningful (terms common to both variants are
+ * skipped); full != 0: true AP sums.  Sums are additive over a partition of the classes, which
+ * is what class-sharded multi-GPU runs reduce (engine.py: compute_rewards(..., shard="classes")).
+ */
+int orie_reward_sums(const orie_index_t *idx, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
+                     void *workspace, size_t workspace_bytes, double *sums, int full, orie_stream_t stream);
+
+/*
+ * Same as orie_reward / orie_reward_sums (reward or sums may be NULL, not both), with CUDA events recorded on
+ * `stream` around each kernel; synchronises and
  * writes kernel_ms_host[4] = {label walk, detection walk, AP integration, finalize} in milliseconds.
  * Measurement aid for bench.py's roofline figure; not part of the reference-facing path.
  */
 int orie_reward_profile(const orie_index_t *idx, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
-                        void *workspace, size_t workspace_bytes, double *reward, double *detail,
+                        void *workspace, size_t workspace_bytes, double *reward, double *sums, int full,
                         orie_stream_t stream, float *kernel_ms_host);
 
 /* Number of kernels this library has launched in this process (all threads). */

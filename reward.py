@@ -9,7 +9,7 @@ behaviour: ``--method ori`` (alias of ``orie --num-ensemble 0``),
 commented line, lib/data.py:60-62), ``--seed`` and ``--ensembles``.
 
 Multi-GPU: ``python -m torch.distributed.run --nproc-per-node N reward.py ...``
-shards the target images over the ranks; rank 0 writes the file.
+shards the classes over the ranks (one all-reduce of the per-target AP sums); rank 0 writes the file.
 """
 import argparse
 import os

@@ -33,6 +33,31 @@ def _worker(rank, world, port, M, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_classes(rank, world, port, M, out_dir):
+    sys.path.insert(0, ROOT)
+    import orie_b200  # noqa: F401
+    from orie_b200.engine import rewards_from_sums
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    sums = torch.rand((M, 3), dtype=torch.float64, generator=g)          # stand-in for this rank's class-shard sums
+    sums[:, 2] = torch.randint(0, 4, (M,), generator=g).double()
+    np.save(os.path.join(out_dir, f"s{rank}.npy"), sums.numpy())
+    dist.all_reduce(sums)
+    np.save(os.path.join(out_dir, f"c{rank}.npy"), rewards_from_sums(sums, 10, 7).numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_class_shard_all_reduce(tmp_path):
+    M = 90
+    mp.spawn(_worker_classes, args=(2, _free_port(), M, str(tmp_path)), nprocs=2, join=True)
+    total = np.load(tmp_path / "s0.npy") + np.load(tmp_path / "s1.npy")
+    nc = total[:, 2]
+    want = np.where(nc > 0, (total[:, 1] - total[:, 0]) / np.maximum(nc * 10, 1) * 8, 0.0)
+    for r in range(2):
+        assert np.allclose(np.load(tmp_path / f"c{r}.npy"), want, rtol=0, atol=1e-12)
+
+
 def test_two_rank_shard_and_gather(tmp_path):
     for M in (70, 500):
         port = _free_port()

@@ -124,3 +124,31 @@ def test_global_memory_membership_table_matches(monkeypatch):
     monkeypatch.delenv("ORIE_WALK_GMEM")
     assert np.array_equal(ref, got)
     eng.close(); eng2.close()
+
+
+def test_class_sharded_sums_add_up():
+    """Multi-GPU decomposition by class, emulated on one GPU: every shard keeps all images and its share of the
+    classes; per-target AP sums of the shards add up to the un-sharded sums, so one all-reduce recovers the rewards."""
+    import torch
+    from orie_b200.engine import Engine, class_shard, clamp_ensemble, rewards_from_sums
+    M, N, world = 150, 60, 3
+    _, pk = make_packed(M=M, seed=55, zipf=0.8)
+    eng = Engine(pk, iouv=O.IOU_05_095)
+    em = O.ensemble_matrix(M, N, 21)
+    ref, ref_detail = eng.orie(N, ens_matrix=em, detail=True)
+    eng.close()
+    for full in (True, False):
+        total = torch.zeros((M, 3), dtype=torch.float64, device="cuda")
+        for r in range(world):
+            e = Engine(class_shard(pk, r, world), iouv=O.IOU_05_095)
+            total += e.orie_sums_device(N, ens_matrix=em, full=full, total_images=M)
+            e.check_status()
+            e.close()
+        got = rewards_from_sums(total, 10, clamp_ensemble(M, N)).cpu().numpy()
+        assert np.abs(got - ref).max() < 1e-11
+        if full:
+            assert np.abs(total.cpu().numpy() - ref_detail).max() < 1e-9
+    # device-drawn ensembles depend on (seed, target, M) only, so every shard draws the same ones
+    a = Engine(class_shard(pk, 0, world), iouv=O.IOU_05).sample_bits(N, seed=3)
+    b = Engine(class_shard(pk, 2, world), iouv=O.IOU_05).sample_bits(N, seed=3)
+    assert np.array_equal(a, b)

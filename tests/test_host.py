@@ -143,3 +143,25 @@ def test_product_package_never_imports_the_oracle():
                 assert "import oracle" not in text and "from oracle" not in text, f
     text = open(os.path.join(ROOT, "reward.py")).read()
     assert "oracle" not in text
+
+
+def test_class_partition_and_reward_formula():
+    ds = synth.make("smoke500", num_images=80, seed=6, zipf=1.0)
+    pk = data.pack(ds.labels, ds.weak, ds.strong)
+    for world in (1, 2, 3, 8, 200):
+        owner = engine.class_partition(pk, world)
+        assert owner.min() >= 0 and owner.max() < world and len(owner) == pk.num_classes
+        rows = 0
+        for r in range(world):
+            sh = engine.class_shard(pk, r, world)
+            assert sh.num_images == pk.num_images and len(sh.w_off) == pk.num_images + 1
+            assert set(sh.class_values.tolist()) == set(pk.class_values[owner == r].tolist())
+            rows += len(sh.w_cls) + len(sh.s_cls) + len(sh.l_cls)
+            if len(sh.w_cls):                                     # rows keep their file order inside an image
+                i = int(np.argmax(np.diff(sh.w_off)))
+                keep = owner[pk.w_cls[pk.w_off[i]:pk.w_off[i + 1]]] == r
+                assert np.array_equal(sh.w_conf[sh.w_off[i]:sh.w_off[i + 1]], pk.w_conf[pk.w_off[i]:pk.w_off[i + 1]][keep])
+        assert rows == len(pk.w_cls) + len(pk.s_cls) + len(pk.l_cls)
+    sums = np.array([[1.0, 2.0, 4.0], [3.0, 1.0, 2.0], [0.0, 0.0, 0.0]])
+    r = engine.rewards_from_sums(sums, 10, 5)
+    assert np.allclose(r, [(2 / 40 - 1 / 40) * 6, (1 / 20 - 3 / 20) * 6, 0.0])
