@@ -247,7 +247,7 @@ def run_b200(args):
     kernel_ms = {"label_walk_ms": [], "walk_ms": [], "ap_ms": [], "finalize_ms": []}
     phase_ms = {"match_index_ms": [], "reward_ms": []}
 
-    def step(seed, record):
+    def step(seed, record, profile=False):
         """match + index + ensemble draw + rewards (+ all-gather) from HBM-resident inputs."""
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
@@ -268,9 +268,16 @@ def run_b200(args):
             _lib.check(lib.orie_ensemble_sample(eng._handle, t0 + a, cnt, Nc, seed, C.c_void_p(bits.data_ptr()), s))
             out_r = C.c_void_p(0) if by_class else C.c_void_p(mine.data_ptr() + 8 * a)
             out_s = C.c_void_p(sums.data_ptr() + 24 * a) if by_class else C.c_void_p(0)
-            _lib.check(lib.orie_reward_profile(eng._handle, t0 + a, cnt, C.c_void_p(bits.data_ptr()), Nc,
-                                               C.c_void_p(ws.data_ptr()), ws.numel(), out_r, out_s, 0, s, part))
-            ms = [x + float(y) for x, y in zip(ms, part)]
+            if profile:      # untimed passes only: events around every kernel, synchronises
+                _lib.check(lib.orie_reward_profile(eng._handle, t0 + a, cnt, C.c_void_p(bits.data_ptr()), Nc,
+                                                   C.c_void_p(ws.data_ptr()), ws.numel(), out_r, out_s, 0, s, part))
+                ms = [x + float(y) for x, y in zip(ms, part)]
+            elif by_class:
+                _lib.check(lib.orie_reward_sums(eng._handle, t0 + a, cnt, C.c_void_p(bits.data_ptr()), Nc,
+                                                C.c_void_p(ws.data_ptr()), ws.numel(), out_s, 0, s))
+            else:
+                _lib.check(lib.orie_reward(eng._handle, t0 + a, cnt, C.c_void_p(bits.data_ptr()), Nc,
+                                           C.c_void_p(ws.data_ptr()), ws.numel(), out_r, C.c_void_p(0), s))
         if by_class:
             dist.all_reduce(sums)                       # 3 doubles per target: AP sums are additive over classes
             gathered[:M].copy_(rewards_from_sums(sums, T, Nc))
@@ -280,9 +287,10 @@ def run_b200(args):
             gathered.copy_(mine)
         e2.record()
         e2.synchronize()
-        if record:
+        if profile:
             for k, v in zip(("label_walk_ms", "walk_ms", "ap_ms", "finalize_ms"), ms):
                 kernel_ms[k].append(float(v))
+        elif record:
             phase_ms["match_index_ms"].append(e0.elapsed_time(e1))
             phase_ms["reward_ms"].append(e1.elapsed_time(e2))
         info = eng.info
@@ -308,6 +316,10 @@ def run_b200(args):
     barrier()
     wall = time.perf_counter() - wall0
     launches = lib.orie_launch_count() - launches0
+    for k in range(min(args.steps, 5)):     # per-kernel durations for the roofline: same step, events around each kernel, untimed
+        flush.fill_(k)
+        torch.cuda.synchronize()
+        step(2000 + k, False, profile=True)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

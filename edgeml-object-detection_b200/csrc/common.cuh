@@ -41,15 +41,43 @@ void count_launches(int n);
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
-// ---- device primitives (sort.cu) -------------------------------------------
-// Stable LSD radix sort of (key, value) pairs on bits [bit_lo, bit_hi) of the key.
-// keys/vals are ping-ponged with the *_tmp buffers; the result always ends in keys/vals.
-// scratch: at least radix_scratch_bytes(n) bytes.
-size_t radix_scratch_bytes(int64_t n);
-int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
-                     int bit_lo, int bit_hi, void *scratch, cudaStream_t st);
-// Exclusive prefix sum of uint32 (in place allowed); total (optional, device) receives the sum.
-size_t scan_scratch_bytes(int64_t n);
-int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *total, void *scratch, cudaStream_t st);
+// ---- device primitive (sort.cu) ---------------------------------------------
+// Stable LSD radix sort of uint32 values (optionally carrying 64-bit keys), all passes in one cooperative
+// launch.  The digit of a pass is 8 bits (or fewer) of
+//   kDigitKey            the item's 64-bit key                  (key passes must come first)
+//   kDigitClass          the class of the value u, a combined row id: u < split ? cls_lo[u] : cls_hi[u - split]
+//   kDigitImageDetector  img[u] * 2 + (u >= split)
+//   kDigitBatchDetector  (img[u] / 32) * 2 + (u >= split)
+// vals_in == nullptr means the identity (value = position).  The sorted values always end in vals_a
+// (vals_a, vals_b: two buffers of n values, distinct from vals_in); keys0 holds the input keys and is
+// overwritten, keys1 is a second buffer of n keys; the sorted keys are not kept.
+// rank_out (optional): rank_out[v] = number of sorted values < rank_split in front of position v.
+enum { kDigitKey = 0, kDigitClass = 1, kDigitImageDetector = 2, kDigitBatchDetector = 3 };
+constexpr int kMaxSortPasses = 12;
+struct SortPass {
+    int kind, shift;
+    uint32_t mask;
+};
+struct SortJob {
+    int64_t n = 0;
+    int npass = 0;
+    SortPass pass[kMaxSortPasses] = {};
+    uint64_t *keys0 = nullptr, *keys1 = nullptr;
+    const uint32_t *vals_in = nullptr;
+    uint32_t *vals_a = nullptr, *vals_b = nullptr;
+    const int32_t *cls_lo = nullptr, *cls_hi = nullptr;
+    const uint32_t *img = nullptr;
+    uint32_t split = 0xffffffffu;
+    uint32_t *rank_out = nullptr;
+    uint32_t rank_split = 0;
+    // filled in by sort_run
+    uint32_t *table = nullptr;
+    unsigned *bar = nullptr;
+    int64_t per = 0;
+};
+int sort_max_blocks(int *out);                    // co-resident CTAs of the sort kernel on the current device
+size_t sort_scratch_bytes(int max_blocks);
+int sort_add_passes(SortJob *job, int kind, int bit_lo, int bit_hi);
+int sort_run(SortJob job, int max_blocks, void *scratch, cudaStream_t st);
 
 }  // namespace orie

@@ -12,12 +12,13 @@
 #include <algorithm>
 #include <vector>
 
+#include "coop.cuh"
 #include "index.cuh"
 
 namespace orie {
 
 // ----------------------------------------------------------------------------
-// small kernels.  "u" is a combined detection id: [0, Dw) weak rows, [Dw, Dw+Ds) strong rows.
+// kernels.  "u" is a combined detection id: [0, Dw) weak rows, [Dw, Dw+Ds) strong rows.
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t conf_desc_key(double c) {
     // order-isomorphic to "descending double": smaller key <=> larger confidence
@@ -32,80 +33,73 @@ struct Dets {
     const double *w_conf, *s_conf;
     const uint16_t *w_tp, *s_tp;
     __device__ __forceinline__ int cls(uint32_t u) const { return u < Dw ? w_cls[u] : s_cls[u - Dw]; }
-    __device__ __forceinline__ double conf(uint32_t u) const { return u < Dw ? w_conf[u] : s_conf[u - Dw]; }
 };
 
-// image of every row of one CSR block (largest i with off[i] <= k)
-__global__ void image_of_row_kernel(const int64_t *__restrict__ off, int64_t M, int64_t n, uint32_t *__restrict__ img,
-                                    int32_t *__restrict__ status) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    int64_t lo = 0, hi = M;
-    while (hi - lo > 1) {
-        int64_t mid = (lo + hi) >> 1;
-        if (off[mid] <= k) lo = mid; else hi = mid;
-    }
-    img[k] = (uint32_t)lo;
-    if (off[lo + 1] - off[lo] > 65535) atomicOr(status, 1);
-}
+// ---- prep: one warp per (image, block) with block in {weak, strong, labels}.  Writes the image of every
+// row, the confidence sort keys, the class histograms (weak / labels drive the layouts, strong is only
+// range-checked), the per-image ground-truth class counts, and validates the inputs.
+//   status bit 0: an image has more than 65535 rows   bit 1: class id out of range   bit 2: off[M] != row count
+struct PrepArgs {
+    int64_t M, C, Dw, Ds, G;
+    const int64_t *w_off, *s_off, *l_off;
+    const int32_t *w_cls, *s_cls, *l_cls;
+    const double *w_conf, *s_conf;
+    uint64_t *keys;      // [Dw + Ds]
+    uint32_t *img_all;   // [Dw + Ds]
+    uint32_t *img_l;     // [G]
+    uint32_t *hist;      // [3][C]: weak, labels, strong
+    uint32_t *gtcnt;     // [M][C], zero on entry
+    int32_t *status;
+    int smem_bins;       // 3 * C if the block-local histogram fits in shared memory, else 0
+};
+constexpr int kPrepThreads = 256;
+constexpr int kPrepMaxSmemBins = 12288;   // 48 KB
 
-__global__ void conf_keys_kernel(const Dets d, int64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
-    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n) return;
-    keys[u] = conf_desc_key(d.conf((uint32_t)u));
-    vals[u] = (uint32_t)u;
-}
-
-enum KeyKind { kKeyClass = 0, kKeyImageDetector = 1, kKeyBatchDetector = 2 };
-
-// re-key the current order for the next stable pass
-template <int KIND>
-__global__ void rekey_kernel(const Dets d, const uint32_t *__restrict__ img_all, const uint32_t *__restrict__ vals, int64_t n,
-                             uint64_t *__restrict__ keys) {
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n) return;
-    const uint32_t u = vals[v];
-    uint64_t k;
-    if (KIND == kKeyClass) k = (uint64_t)(uint32_t)d.cls(u);
-    else if (KIND == kKeyImageDetector) k = ((uint64_t)img_all[u] << 1) | (u >= d.Dw);
-    else k = ((uint64_t)(img_all[u] >> 5) << 1) | (u >= d.Dw);
-    keys[v] = k;
-}
-
-// class histogram: per-block shared-memory bins (C <= kHistSmemBins), flushed with one global atomic per
-// non-empty bin; plain global atomics beyond that
-constexpr int kHistSmemBins = 8192;
-constexpr int kHistItemsPerBlock = 8192;
-__global__ void class_hist_kernel(const int32_t *__restrict__ cls, int64_t n, int64_t C, uint32_t *__restrict__ hist,
-                                  int32_t *__restrict__ status) {
+__global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepArgs a) {
     extern __shared__ uint32_t bins[];
-    const bool local = C <= kHistSmemBins;
-    if (local) {
-        for (int i = threadIdx.x; i < C; i += blockDim.x) bins[i] = 0;
-        __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < a.smem_bins; i += kPrepThreads) bins[i] = 0;
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (a.w_off[a.M] != a.Dw || a.s_off[a.M] != a.Ds || a.l_off[a.M] != a.G))
+        atomicOr(a.status, 4);
+    const int64_t nwarps = (int64_t)gridDim.x * (kPrepThreads / 32);
+    for (int64_t w = (int64_t)blockIdx.x * (kPrepThreads / 32) + (threadIdx.x >> 5); w < 3 * a.M; w += nwarps) {
+        const int blk = (int)(w / a.M);            // 0 weak, 1 labels, 2 strong (the order of the histograms)
+        const int64_t im = w - blk * a.M;
+        const int64_t *off = blk == 0 ? a.w_off : (blk == 1 ? a.l_off : a.s_off);
+        const int32_t *cls = blk == 0 ? a.w_cls : (blk == 1 ? a.l_cls : a.s_cls);
+        const int64_t r0 = off[im], r1 = off[im + 1];
+        if (r1 - r0 > 65535 && lane == 0) atomicOr(a.status, 1);
+        for (int64_t r = r0 + lane; r < r1; r += 32) {
+            const int c = cls[r];
+            const bool ok = c >= 0 && c < a.C;
+            if (!ok) atomicOr(a.status, 2);
+            else if (a.smem_bins) atomicAdd(&bins[blk * a.C + c], 1u);
+            else atomicAdd(&a.hist[blk * a.C + c], 1u);
+            if (blk == 1) {
+                a.img_l[r] = (uint32_t)im;
+                if (ok) atomicAdd(&a.gtcnt[im * a.C + c], 1u);
+            } else {
+                const int64_t u = blk == 0 ? r : a.Dw + r;
+                a.keys[u] = conf_desc_key(blk == 0 ? a.w_conf[r] : a.s_conf[r]);
+                a.img_all[u] = (uint32_t)im;
+            }
+        }
     }
-    const int64_t base = (int64_t)blockIdx.x * kHistItemsPerBlock;
-    const int64_t end = base + kHistItemsPerBlock < n ? base + kHistItemsPerBlock : n;
-    for (int64_t k = base + threadIdx.x; k < end; k += blockDim.x) {
-        const int c = cls[k];
-        if (c < 0 || c >= C) { atomicOr(status, 2); continue; }
-        atomicAdd(local ? &bins[c] : &hist[c], 1u);
-    }
-    if (local) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < C; i += blockDim.x)
-            if (bins[i]) atomicAdd(&hist[i], bins[i]);
-    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.smem_bins; i += kPrepThreads)
+        if (bins[i]) atomicAdd(&a.hist[i], bins[i]);
 }
 
-__global__ void fill_u32_kernel(uint32_t *__restrict__ p, int64_t n, uint32_t v) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) p[k] = v;
-}
-
-__global__ void weak_flag_kernel(const uint32_t *__restrict__ order, int64_t n, uint32_t Dw, uint32_t *__restrict__ flag) {
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < n) flag[v] = order[v] < Dw ? 1u : 0u;
+// padding slots: image M (never a member), no true positive
+__global__ void init_slots_kernel(uint32_t *__restrict__ slot_img, uint16_t *__restrict__ slot_tp, int64_t P,
+                                  uint32_t *__restrict__ lab_slot_img, int64_t PL, uint32_t M) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += stride) {
+        slot_img[k] = M;
+        slot_tp[k] = 0;
+    }
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < PL; k += stride) lab_slot_img[k] = M;
 }
 
 // position v of the combined (class, conf desc) order -> slot (weak) / insertion slot (strong).
@@ -126,34 +120,57 @@ __global__ void place_slots_kernel(const Dets d, const uint32_t *__restrict__ or
     }
 }
 
-// one warp per chunk
-__global__ void event_bits_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks, uint32_t *__restrict__ evbits,
-                                  uint32_t *__restrict__ evcnt) {
-    int64_t ch = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (ch >= nchunks) return;
-    const int lane = threadIdx.x & 31;
-    unsigned b = __ballot_sync(kFull, slot_tp[ch * 32 + lane] != 0);
-    if (lane == 0) { evbits[ch] = b; evcnt[ch] = __popc(b); }
+// ---- event table in one cooperative launch: per chunk the slots holding a true positive (evbits), the
+// chunk's first event (evbase = exclusive scan of the counts), the compacted masks (evmask), the total,
+// and each segment's first event.
+constexpr int kEvThreads = 512;
+__global__ void __launch_bounds__(kEvThreads)
+events_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks, int64_t per, uint32_t *__restrict__ evbits,
+              uint32_t *evbase, uint16_t *__restrict__ evmask, const int32_t *__restrict__ seg_chunk0, int64_t S,
+              uint32_t *__restrict__ seg_ev0, uint32_t *table, unsigned *bar, uint32_t *__restrict__ total_out) {
+    __shared__ uint32_t ws[kEvThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned epoch = 0;
+    const int64_t c0 = (int64_t)blockIdx.x * per, c1 = c0 + per < nchunks ? c0 + per : nchunks;
+    const int64_t cw = (per + kEvThreads / 32 - 1) / (kEvThreads / 32);
+    const int64_t w0 = c0 + warp * cw, w1 = w0 + cw < c1 ? w0 + cw : c1;
+    uint32_t mine = 0;
+    for (int64_t ch = w0; ch < w1; ++ch) {
+        const unsigned b = __ballot_sync(kFull, slot_tp[ch * 32 + lane] != 0);
+        if (lane == 0) evbits[ch] = b;
+        mine += __popc(b);
+    }
+    uint32_t cta_total;
+    const uint32_t excl = block_exclusive_scan<kEvThreads>(lane == 0 ? mine : 0u, ws, &cta_total);
+    const uint32_t warp_base = __shfl_sync(kFull, excl, 0);
+    if (threadIdx.x == 0) __stcg(table + blockIdx.x, cta_total);
+    grid_sync(bar, epoch);
+    uint32_t before = 0, all = 0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kEvThreads) {
+        const uint32_t v = __ldcg(table + b);
+        all += v;
+        before += b < (int)blockIdx.x ? v : 0u;
+    }
+    uint32_t carry, grand;
+    block_exclusive_scan<kEvThreads>(before, ws, &carry);
+    block_exclusive_scan<kEvThreads>(all, ws, &grand);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total_out = grand;
+    uint32_t run = carry + warp_base;
+    for (int64_t ch = w0; ch < w1; ++ch) {
+        const uint16_t tp = slot_tp[ch * 32 + lane];
+        const unsigned b = __ballot_sync(kFull, tp != 0);
+        if (lane == 0) evbase[ch] = run;
+        if (tp) evmask[run + __popc(b & ((1u << lane) - 1u))] = tp;
+        run += __popc(b);
+    }
+    grid_sync(bar, epoch);
+    for (int64_t s = (int64_t)blockIdx.x * kEvThreads + threadIdx.x; s < S; s += (int64_t)gridDim.x * kEvThreads)
+        seg_ev0[s] = __ldcg(evbase + seg_chunk0[s]);
 }
 
-__global__ void event_mask_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks,
-                                  const uint32_t *__restrict__ evbits, const uint32_t *__restrict__ evbase,
-                                  uint16_t *__restrict__ evmask) {
-    int64_t ch = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (ch >= nchunks) return;
-    const int lane = threadIdx.x & 31;
-    const unsigned b = evbits[ch];
-    if ((b >> lane) & 1u) evmask[evbase[ch] + __popc(b & ((1u << lane) - 1u))] = slot_tp[ch * 32 + lane];
-}
-
-__global__ void gather_seg_ev0_kernel(const int32_t *__restrict__ seg_chunk0, int64_t S, const uint32_t *__restrict__ evbase,
-                                      uint32_t *__restrict__ seg_ev0) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < S) seg_ev0[s] = evbase[seg_chunk0[s]];
-}
-
-// Image-major order (key = image * 2 + is_strong): image i occupies [w_off[i] + s_off[i], ...), its weak
-// rows first.  Fills the own lists (aligned with w_off / s_off) and remembers each row's own position.
+// Image-major order (sorted by image * 2 + is_strong, stable on the (class, conf) order): image i occupies
+// [w_off[i] + s_off[i], ...), its weak rows first.  Fills the own lists (aligned with w_off / s_off) and
+// remembers each row's own position.
 __global__ void own_fill_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ img_all,
                                 int64_t n, const int64_t *__restrict__ w_off, const int64_t *__restrict__ s_off,
                                 const uint32_t *__restrict__ q_of_det, uint32_t *__restrict__ own_w_q,
@@ -176,23 +193,31 @@ __global__ void own_fill_kernel(const Dets d, const uint32_t *__restrict__ order
     }
 }
 
-// class start table of every image's own list: cs[img][c] = first local index with class >= c
-__global__ void own_class_start_kernel(const uint16_t *__restrict__ own_c, const uint32_t *__restrict__ img_of_row, int64_t n,
-                                       const int64_t *__restrict__ off, int64_t C, uint16_t *__restrict__ cs) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t im = img_of_row[i];
-    const int c = own_c[i];
-    const int64_t a = off[im], b = off[im + 1];
-    uint16_t *row = cs + (int64_t)im * (C + 1);
-    const int local = (int)(i - a);
-    if (i == a)
-        for (int cc = 0; cc <= c; ++cc) row[cc] = 0;
-    const int cnext = (i + 1 < b) ? (int)own_c[i + 1] : (int)C;
-    for (int cc = c + 1; cc <= cnext; ++cc) row[cc] = (uint16_t)(local + 1);
+// class start table of every image's own list (ascending by class): cs[img][c] = first local index with
+// class >= c, c in [0, C].  One warp per (detector, image); every entry of the row is written.
+__global__ void own_class_start_kernel(const uint16_t *__restrict__ own_w_c, const int64_t *__restrict__ w_off,
+                                       uint16_t *__restrict__ w_cs, const uint16_t *__restrict__ own_s_c,
+                                       const int64_t *__restrict__ s_off, uint16_t *__restrict__ s_cs, int64_t M, int64_t C) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= 2 * M) return;
+    const int lane = threadIdx.x & 31;
+    const bool strong = w >= M;
+    const int64_t im = strong ? w - M : w;
+    const int64_t *off = strong ? s_off : w_off;
+    const uint16_t *list = (strong ? own_s_c : own_w_c) + off[im];
+    const int len = (int)(off[im + 1] - off[im]);
+    uint16_t *row = (strong ? s_cs : w_cs) + im * (C + 1);
+    for (int c = lane; c <= C; c += 32) {
+        int lo = 0, hi = len;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)list[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        row[c] = (uint16_t)lo;
+    }
 }
 
-// Batch-major order (key = (image / 32) * 2 + is_strong): batch b occupies [w_off[32b] + s_off[32b], ...),
+// Batch-major order (sorted by (image / 32) * 2 + is_strong): batch b occupies [w_off[32b] + s_off[32b], ...),
 // its weak rows first, each part ascending by query slot.
 __global__ void batch_query_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ img_all,
                                    int64_t n, int64_t M, const int64_t *__restrict__ w_off, const int64_t *__restrict__ s_off,
@@ -211,12 +236,18 @@ __global__ void batch_query_kernel(const Dets d, const uint32_t *__restrict__ or
     else bq_s[s_off[i0] + (local - nw)] = e;
 }
 
-// bqoff[b][s] = first entry of batch b with q >= first slot of segment s  (s == S: end of the batch)
-__global__ void batch_query_offsets_kernel(const uint2 *__restrict__ bq, const int64_t *__restrict__ off, int64_t M,
-                                           int64_t nbatch, const int32_t *__restrict__ seg_chunk0, int64_t S,
-                                           uint32_t *__restrict__ bqoff) {
+// bqoff[b][s] = first entry of batch b with q >= first slot of segment s  (s == S: end of the batch); both detectors
+__global__ void batch_query_offsets_kernel(const uint2 *__restrict__ bq_w, const int64_t *__restrict__ w_off,
+                                           uint32_t *__restrict__ bqoff_w, const uint2 *__restrict__ bq_s,
+                                           const int64_t *__restrict__ s_off, uint32_t *__restrict__ bqoff_s, int64_t M,
+                                           int64_t nbatch, const int32_t *__restrict__ seg_chunk0, int64_t S) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nbatch * (S + 1)) return;
+    const int64_t per = nbatch * (S + 1);
+    if (k >= 2 * per) return;
+    const bool strong = k >= per;
+    if (strong) k -= per;
+    const uint2 *bq = strong ? bq_s : bq_w;
+    const int64_t *off = strong ? s_off : w_off;
     const int64_t b = k / (S + 1), s = k % (S + 1);
     const int64_t i0 = b * 32 < M ? b * 32 : M, i1 = (b + 1) * 32 < M ? (b + 1) * 32 : M;
     int64_t lo = off[i0], hi = off[i1];
@@ -229,26 +260,18 @@ __global__ void batch_query_offsets_kernel(const uint2 *__restrict__ bq, const i
     } else {
         lo = hi;
     }
-    bqoff[k] = (uint32_t)lo;
+    (strong ? bqoff_s : bqoff_w)[k] = (uint32_t)lo;
 }
 
-__global__ void place_labels_kernel(const uint64_t *__restrict__ keys_sorted, const uint32_t *__restrict__ img_sorted,
-                                    int64_t n, const uint32_t *__restrict__ cls_off, const uint32_t *__restrict__ pad_off,
-                                    uint32_t *__restrict__ slot_img) {
+// r-th label in class order -> its slot of the padded label stream
+__global__ void place_labels_kernel(const uint32_t *__restrict__ lorder, const int32_t *__restrict__ l_cls,
+                                    const uint32_t *__restrict__ img_l, int64_t n, const uint32_t *__restrict__ cls_off,
+                                    const uint32_t *__restrict__ pad_off, uint32_t *__restrict__ slot_img) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
-    const int c = (int)keys_sorted[r];
-    slot_img[pad_off[c] + ((uint32_t)r - cls_off[c])] = img_sorted[r];
-}
-
-__global__ void label_keys_kernel(const int32_t *__restrict__ cls, const uint32_t *__restrict__ img, int64_t n, int64_t C,
-                                  uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ gtcnt) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int c = cls[k];
-    keys[k] = (uint64_t)(uint32_t)c;
-    vals[k] = img[k];
-    if (c >= 0 && c < C) atomicAdd(&gtcnt[(int64_t)img[k] * C + c], 1u);
+    const uint32_t g = lorder[r];
+    const int c = l_cls[g];
+    slot_img[pad_off[c] + ((uint32_t)r - cls_off[c])] = img_l[g];
 }
 
 static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
@@ -257,37 +280,49 @@ static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
     return b;
 }
 
-// Allocations are stream-ordered (cudaMallocAsync on the device's default pool, whose release
-// threshold is raised once so that rebuilding an index does not go back to the OS every time).
+// Stream-ordered arena: the sizes are collected first, then ONE cudaMallocAsync backs all of them (the
+// device's default pool keeps its memory between builds: the release threshold is raised once).
+struct Arena {
+    struct Item {
+        void **p;
+        size_t bytes;
+    };
+    std::vector<Item> items;
+    template <typename Tp>
+    void add(Tp **p, int64_t count) {
+        items.push_back({(void **)p, (size_t)round_up(std::max<int64_t>(count, 1) * (int64_t)sizeof(Tp), 256)});
+    }
+    int commit(cudaStream_t st, void **base, size_t *bytes) {
+        size_t total = 0;
+        for (auto &it : items) total += it.bytes;
+        void *q = nullptr;
+        ORIE_CUDA(cudaMallocAsync(&q, std::max<size_t>(total, 256), st));
+        size_t at = 0;
+        for (auto &it : items) {
+            *it.p = (char *)q + at;
+            at += it.bytes;
+        }
+        *base = q;
+        if (bytes) *bytes = total;
+        items.clear();
+        return ORIE_OK;
+    }
+};
+
 struct Builder {
     orie_index *ix;
     cudaStream_t st;
-    std::vector<void *> temps;
+    void *temp_base = nullptr;
     ~Builder() {
         cudaStreamSynchronize(st);
-        for (void *p : temps) cudaFreeAsync(p, st);
+        if (temp_base) cudaFreeAsync(temp_base, st);
     }
-    template <typename Tp>
-    int temp(Tp **p, int64_t count) {
-        void *q = nullptr;
-        ORIE_CUDA(cudaMallocAsync(&q, (size_t)std::max<int64_t>(count, 1) * sizeof(Tp), st));
-        temps.push_back(q);
-        *p = (Tp *)q;
-        return ORIE_OK;
-    }
-    template <typename Tp>
-    int keep(Tp **p, int64_t count) {
-        void *q = nullptr;
-        size_t bytes = (size_t)std::max<int64_t>(count, 1) * sizeof(Tp);
-        ORIE_CUDA(cudaMallocAsync(&q, bytes, st));
-        if (ix->n_allocs >= (int)(sizeof(ix->allocs) / sizeof(ix->allocs[0]))) {
-            cudaFreeAsync(q, st);
-            set_error("orie_index_build: allocation table full");
-            return ORIE_EINVAL;
-        }
-        ix->allocs[ix->n_allocs++] = q;
+    int keep(Arena &a) {
+        void *base = nullptr;
+        size_t bytes = 0;
+        ORIE_TRY(a.commit(st, &base, &bytes));
+        ix->allocs[ix->n_allocs++] = base;      // at most three arenas per index
         ix->device_bytes += (int64_t)bytes;
-        *p = (Tp *)q;
         return ORIE_OK;
     }
 };
@@ -327,14 +362,26 @@ static StreamLayout make_layout(const uint32_t *cnt, int64_t C, int extra_pad, i
     return L;
 }
 
-template <typename Tp>
-static int upload(Builder &B, Tp **dst, const std::vector<Tp> &src, bool keep) {
-    if (keep) ORIE_TRY(B.keep(dst, (int64_t)src.size()));
-    else ORIE_TRY(B.temp(dst, (int64_t)src.size()));
-    if (!src.empty())
-        ORIE_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(Tp), cudaMemcpyHostToDevice, B.st));
-    return ORIE_OK;
-}
+// the host-built tables travel in one buffer / one copy
+struct Tables {
+    std::vector<uint32_t> words;
+    struct Ref {
+        void **p;
+        size_t at;
+    };
+    std::vector<Ref> refs;
+    template <typename Tp, typename Vp>
+    void add(Tp **p, const std::vector<Vp> &v) {
+        static_assert(sizeof(Vp) == 4, "32-bit tables only");
+        refs.push_back({(void **)p, words.size()});
+        const size_t n = v.size();
+        words.resize(words.size() + (size_t)round_up(std::max<int64_t>((int64_t)n, 1), 64));
+        if (n) memcpy(words.data() + refs.back().at, v.data(), n * 4);
+    }
+    void bind(uint32_t *base) {
+        for (auto &r : refs) *r.p = base + r.at;
+    }
+};
 
 static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                  const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
@@ -342,12 +389,11 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     // host staging buffers are declared before the Builder so that they outlive its destructor, which
     // synchronises the stream (asynchronous copies from / into them may still be in flight on error paths)
     const int64_t M = ix->M, C = ix->C;
-    std::vector<uint32_t> h_hist(2 * C);
+    std::vector<uint32_t> h_meta(3 * C + 1);
     std::vector<int32_t> cls_order(C);
     StreamLayout LD, LL;
-    int32_t h_status = 0;
+    Tables tab;
     uint32_t h_total = 0;
-    int64_t tails[3];
     Builder B{ix, st};
     {
         int dev = 0;
@@ -357,7 +403,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         ORIE_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
         ORIE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
     }
-    // ---- sizes: given by the caller; off[M] of each block is read back with the class counts and cross-checked
+    // ---- sizes: given by the caller; off[M] of each block is cross-checked on the device (status bit 2)
     const int64_t Dw = ix->Dw, Ds = ix->Ds, G = ix->G;
     if (Dw < 0 || Ds < 0 || G < 0 || Dw >= ((int64_t)1 << 27) || Ds >= ((int64_t)1 << 27) || G >= ((int64_t)1 << 31)) {
         set_error("orie_index_build: row counts out of range (weak %lld, strong %lld, labels %lld; limit 2^27-1 detections per detector)",
@@ -367,86 +413,107 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     const int64_t n = Dw + Ds;
     const int64_t Nmax = std::max<int64_t>(std::max(n, G), 1);
     const Dets dets{Dw, Ds, w_cls, s_cls, w_conf, s_conf, w_tp, s_tp};
+    int sort_blocks = 0, ev_blocks = 0;
+    ORIE_TRY(sort_max_blocks(&sort_blocks));
+    ORIE_TRY(coop_max_blocks(events_kernel, kEvThreads, 0, &ev_blocks));
 
-    ORIE_TRY(B.keep(&ix->w_off, M + 1));
-    ORIE_TRY(B.keep(&ix->s_off, M + 1));
+    // ---- first part of the index (sizes known up front) and the temporaries, one allocation each
+    Arena A;
+    A.add(&ix->w_off, M + 1);
+    A.add(&ix->s_off, M + 1);
+    A.add(&ix->own_w_q, Dw);
+    A.add(&ix->own_w_m, Dw);
+    A.add(&ix->own_s_q, Ds);
+    A.add(&ix->own_s_m, Ds);
+    A.add(&ix->own_w_cs, M * (C + 1));
+    A.add(&ix->own_s_cs, M * (C + 1));
+    A.add(&ix->bq_w, Dw);
+    A.add(&ix->bq_s, Ds);
+    A.add(&ix->evmask, Dw);              // events <= weak detections
+    A.add(&ix->gtcnt, M * C);
+    ORIE_TRY(B.keep(A));
+
+    uint64_t *keys, *keys_tmp;
+    uint32_t *vtmp, *img_all, *img_l, *order, *ord_img, *ord_bat, *lorder, *meta, *wpre, *q_of_det, *ownpos, *d_total;
+    uint16_t *own_w_c, *own_s_c;
+    char *scratch;
+    A.add(&keys, n);
+    A.add(&keys_tmp, n);
+    A.add(&vtmp, Nmax);
+    A.add(&img_all, n);
+    A.add(&img_l, G);
+    A.add(&order, n);
+    A.add(&ord_img, n);
+    A.add(&ord_bat, n);
+    A.add(&lorder, G);
+    A.add(&meta, 3 * C + 1);
+    A.add(&wpre, n);
+    A.add(&q_of_det, n);
+    A.add(&ownpos, n);
+    A.add(&own_w_c, Dw);
+    A.add(&own_s_c, Ds);
+    A.add(&d_total, 1);
+    A.add(&scratch, (int64_t)std::max(sort_scratch_bytes(sort_blocks), (size_t)ev_blocks * 4 + 256));
+    ORIE_TRY(A.commit(st, &B.temp_base, nullptr));
+    int32_t *status = (int32_t *)(meta + 3 * C);
+
     ORIE_CUDA(cudaMemcpyAsync(ix->w_off, w_off, (size_t)(M + 1) * 8, cudaMemcpyDeviceToDevice, st));
     ORIE_CUDA(cudaMemcpyAsync(ix->s_off, s_off, (size_t)(M + 1) * 8, cudaMemcpyDeviceToDevice, st));
-
-    // ---- temporaries
-    uint64_t *keys, *keys_tmp;
-    uint32_t *vals, *vals_tmp, *img_all, *img_l, *order, *hist, *wpre, *q_of_det, *ownpos, *evcnt, *d_total;
-    uint16_t *slot_tp, *own_w_c, *own_s_c;
-    int32_t *status;
-    char *rscratch, *sscratch;
-    ORIE_TRY(B.temp(&keys, Nmax));
-    ORIE_TRY(B.temp(&keys_tmp, Nmax));
-    ORIE_TRY(B.temp(&vals, Nmax));
-    ORIE_TRY(B.temp(&vals_tmp, Nmax));
-    ORIE_TRY(B.temp(&img_all, n));
-    ORIE_TRY(B.temp(&img_l, G));
-    ORIE_TRY(B.temp(&order, n));
-    ORIE_TRY(B.temp(&hist, 3 * C));
-    ORIE_TRY(B.temp(&wpre, n));
-    ORIE_TRY(B.temp(&q_of_det, n));
-    ORIE_TRY(B.temp(&ownpos, n));
-    ORIE_TRY(B.temp(&own_w_c, Dw));
-    ORIE_TRY(B.temp(&own_s_c, Ds));
-    ORIE_TRY(B.temp(&status, 1));
-    ORIE_TRY(B.temp(&d_total, 1));
-    ORIE_TRY(B.temp(&rscratch, (int64_t)radix_scratch_bytes(Nmax)));
-    ORIE_TRY(B.temp(&sscratch, (int64_t)scan_scratch_bytes(Nmax)));
-    ORIE_CUDA(cudaMemsetAsync(status, 0, 4, st));
-    ORIE_CUDA(cudaMemsetAsync(hist, 0, (size_t)(3 * C) * 4, st));
+    ORIE_CUDA(cudaMemsetAsync(meta, 0, (size_t)(3 * C + 1) * 4, st));
+    ORIE_CUDA(cudaMemsetAsync(ix->gtcnt, 0, (size_t)(M * C) * 4, st));
 
     const int cbits = bits_for(C), ibits = bits_for(M) + 1, bbits = bits_for(ix->nbatch) + 1;
 
-    // ---- image of every row; class histograms (weak / labels drive the layouts, strong is range-checked)
-    const size_t hist_smem = C <= kHistSmemBins ? (size_t)C * 4 : 0;
-    if (Dw) {
-        image_of_row_kernel<<<grid_for(Dw), 256, 0, st>>>(w_off, M, Dw, img_all, status);
-        ORIE_LAUNCH_CHECK();
-        class_hist_kernel<<<grid_for(Dw, kHistItemsPerBlock), 256, hist_smem, st>>>(w_cls, Dw, C, hist, status);
-        ORIE_LAUNCH_CHECK();
-    }
-    if (Ds) {
-        image_of_row_kernel<<<grid_for(Ds), 256, 0, st>>>(s_off, M, Ds, img_all + Dw, status);
-        ORIE_LAUNCH_CHECK();
-        class_hist_kernel<<<grid_for(Ds, kHistItemsPerBlock), 256, hist_smem, st>>>(s_cls, Ds, C, hist + 2 * C, status);
-        ORIE_LAUNCH_CHECK();
-    }
-    if (G) {
-        image_of_row_kernel<<<grid_for(G), 256, 0, st>>>(l_off, M, G, img_l, status);
-        ORIE_LAUNCH_CHECK();
-        class_hist_kernel<<<grid_for(G, kHistItemsPerBlock), 256, hist_smem, st>>>(l_cls, G, C, hist + C, status);
+    // ---- prep: images of rows, confidence keys, class histograms, ground-truth counts, validation
+    {
+        PrepArgs pa{M, C, Dw, Ds, G, w_off, s_off, l_off, w_cls, s_cls, l_cls, w_conf, s_conf,
+                    keys, img_all, img_l, meta, ix->gtcnt, status, 3 * C <= kPrepMaxSmemBins ? (int)(3 * C) : 0};
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(3 * M, kPrepThreads / 32), 148 * 8);
+        prep_kernel<<<grid, kPrepThreads, (size_t)pa.smem_bins * 4, st>>>(pa);
         ORIE_LAUNCH_CHECK();
     }
 
     // ---- ONE sort of all detections: confidence desc (64-bit key), then class (stable).  Weak rows precede
-    //      strong rows in the input, so on exact confidence ties weak sorts first (stable concatenation order).
+    //      strong rows in the id space, so on exact confidence ties weak sorts first, then image, then row.
+    //      The epilogue ranks every position among the weak detections (wpre).
     if (n) {
-        conf_keys_kernel<<<grid_for(n), 256, 0, st>>>(dets, n, keys, vals);
-        ORIE_LAUNCH_CHECK();
-        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 0, 64, rscratch, st));
-        rekey_kernel<kKeyClass><<<grid_for(n), 256, 0, st>>>(dets, img_all, vals, n, keys);
-        ORIE_LAUNCH_CHECK();
-        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 0, cbits, rscratch, st));
-        ORIE_CUDA(cudaMemcpyAsync(order, vals, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-        weak_flag_kernel<<<grid_for(n), 256, 0, st>>>(order, n, (uint32_t)Dw, wpre);
-        ORIE_LAUNCH_CHECK();
-        ORIE_TRY(exclusive_scan_u32(wpre, wpre, n, nullptr, sscratch, st));
+        SortJob j;
+        j.n = n;
+        j.keys0 = keys; j.keys1 = keys_tmp;
+        j.vals_a = order; j.vals_b = vtmp;
+        j.cls_lo = w_cls; j.cls_hi = s_cls; j.split = (uint32_t)Dw;
+        j.rank_out = wpre; j.rank_split = (uint32_t)Dw;
+        ORIE_TRY(sort_add_passes(&j, kDigitKey, 0, 64));
+        ORIE_TRY(sort_add_passes(&j, kDigitClass, 0, cbits));
+        ORIE_TRY(sort_run(j, sort_blocks, scratch, st));
+        // the same order regrouped by image and by 32-image batch (both detectors at once, weak first)
+        SortJob r;
+        r.n = n;
+        r.vals_in = order; r.vals_a = ord_img; r.vals_b = vtmp;
+        r.img = img_all; r.split = (uint32_t)Dw;
+        ORIE_TRY(sort_add_passes(&r, kDigitImageDetector, 0, ibits));
+        ORIE_TRY(sort_run(r, sort_blocks, scratch, st));
+        r.npass = 0;
+        r.vals_a = ord_bat;
+        ORIE_TRY(sort_add_passes(&r, kDigitBatchDetector, 0, bbits));
+        ORIE_TRY(sort_run(r, sort_blocks, scratch, st));
+    }
+    if (G) {
+        SortJob j;
+        j.n = G;
+        j.vals_a = lorder; j.vals_b = vtmp;
+        j.cls_lo = l_cls;
+        ORIE_TRY(sort_add_passes(&j, kDigitClass, 0, cbits));
+        ORIE_TRY(sort_run(j, sort_blocks, scratch, st));
     }
 
     // ---- host: class counts -> padded layouts and segment tables
-    ORIE_CUDA(cudaMemcpyAsync(h_hist.data(), hist, (size_t)(2 * C) * 4, cudaMemcpyDeviceToHost, st));
-    ORIE_CUDA(cudaMemcpyAsync(&h_status, status, 4, cudaMemcpyDeviceToHost, st));
-    ORIE_CUDA(cudaMemcpyAsync(&tails[0], w_off + M, 8, cudaMemcpyDeviceToHost, st));
-    ORIE_CUDA(cudaMemcpyAsync(&tails[1], s_off + M, 8, cudaMemcpyDeviceToHost, st));
-    ORIE_CUDA(cudaMemcpyAsync(&tails[2], l_off + M, 8, cudaMemcpyDeviceToHost, st));
+    ORIE_CUDA(cudaMemcpyAsync(h_meta.data(), meta, (size_t)(3 * C + 1) * 4, cudaMemcpyDeviceToHost, st));
     ORIE_CUDA(cudaStreamSynchronize(st));
-    if (tails[0] != Dw || tails[1] != Ds || tails[2] != G) {
-        set_error("orie_index_build: row counts (%lld, %lld, %lld) do not match the offset arrays (%lld, %lld, %lld)",
-                  (long long)Dw, (long long)Ds, (long long)G, (long long)tails[0], (long long)tails[1], (long long)tails[2]);
+    const uint32_t h_status = h_meta[3 * C];
+    if (h_status & 4) {
+        set_error("orie_index_build: row counts (%lld, %lld, %lld) do not match the offset arrays",
+                  (long long)Dw, (long long)Ds, (long long)G);
         return ORIE_EDATA;
     }
     if (h_status & 2) {
@@ -457,6 +524,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         set_error("orie_index_build: an image has more than 65535 rows in one file");
         return ORIE_ELIMIT;
     }
+    const uint32_t *h_hist = h_meta.data();
     int64_t raw_chunks = 0;
     for (int64_t c = 0; c < C; ++c) raw_chunks += ceil_div((int64_t)h_hist[c] + 1, kChunk);
     // Segment length: about two segments per average class (measured best for both the walk's load balance
@@ -466,8 +534,8 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     int seg_chunks = seg_chunks_req > 0 ? seg_chunks_req
                                         : (int)std::min<int64_t>(512, std::max<int64_t>(16, ceil_div(raw_chunks, seg_target)));
     ix->seg_chunks = seg_chunks;
-    LD = make_layout(h_hist.data(), C, 1, seg_chunks);
-    LL = make_layout(h_hist.data() + C, C, 0, seg_chunks);
+    LD = make_layout(h_hist, C, 1, seg_chunks);
+    LL = make_layout(h_hist + C, C, 0, seg_chunks);
     ix->P = LD.P; ix->nchunks = LD.P / kChunk; ix->S = (int64_t)LD.seg_chunk0.size();
     ix->PL = LL.P; ix->nchunksL = LL.P / kChunk; ix->SL = (int64_t)LL.seg_chunk0.size();
     if (ix->P >= ((int64_t)1 << 31)) {
@@ -476,30 +544,38 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     }
     for (int64_t c = 0; c < C; ++c) cls_order[c] = (int32_t)c;
     std::stable_sort(cls_order.begin(), cls_order.end(), [&](int32_t a, int32_t b) { return h_hist[a] > h_hist[b]; });
-    uint32_t *d_cls_off, *d_pad_off, *d_lcls_off, *d_lpad_off;
-    ORIE_TRY(upload(B, &d_cls_off, LD.cls_off, false));
-    ORIE_TRY(upload(B, &d_pad_off, LD.pad_off, false));
-    ORIE_TRY(upload(B, &d_lcls_off, LL.cls_off, false));
-    ORIE_TRY(upload(B, &d_lpad_off, LL.pad_off, false));
-    ORIE_TRY(upload(B, &ix->seg_chunk0, LD.seg_chunk0, true));
-    ORIE_TRY(upload(B, &ix->seg_nch, LD.seg_nch, true));
-    ORIE_TRY(upload(B, &ix->cls_seg0, LD.cls_seg0, true));
-    ORIE_TRY(upload(B, &ix->cls_order, cls_order, true));
-    ORIE_TRY(upload(B, &ix->lseg_chunk0, LL.seg_chunk0, true));
-    ORIE_TRY(upload(B, &ix->lseg_nch, LL.seg_nch, true));
-    ORIE_TRY(upload(B, &ix->lcls_seg0, LL.cls_seg0, true));
-    // the host vectors stay alive until the end of this function, which ends with a stream synchronisation
+    uint32_t *d_cls_off, *d_pad_off, *d_lcls_off, *d_lpad_off, *d_tables;
+    tab.add(&d_cls_off, LD.cls_off);
+    tab.add(&d_pad_off, LD.pad_off);
+    tab.add(&d_lcls_off, LL.cls_off);
+    tab.add(&d_lpad_off, LL.pad_off);
+    tab.add(&ix->seg_chunk0, LD.seg_chunk0);
+    tab.add(&ix->seg_nch, LD.seg_nch);
+    tab.add(&ix->cls_seg0, LD.cls_seg0);
+    tab.add(&ix->cls_order, cls_order);
+    tab.add(&ix->lseg_chunk0, LL.seg_chunk0);
+    tab.add(&ix->lseg_nch, LL.seg_nch);
+    tab.add(&ix->lcls_seg0, LL.cls_seg0);
+
+    // ---- second part of the index (sizes depend on the class counts)
+    uint16_t *slot_tp;
+    A.add(&d_tables, (int64_t)tab.words.size());
+    A.add(&ix->slot_img, ix->P);
+    A.add(&ix->evbits, ix->nchunks);
+    A.add(&ix->evbase, ix->nchunks);
+    A.add(&ix->seg_ev0, ix->S);
+    A.add(&ix->bqoff_w, ix->nbatch * (ix->S + 1));
+    A.add(&ix->bqoff_s, ix->nbatch * (ix->S + 1));
+    A.add(&ix->lab_slot_img, ix->PL);
+    A.add(&slot_tp, ix->P);              // only needed during the build; rides along (2 bytes per slot)
+    ORIE_TRY(B.keep(A));
+    tab.bind(d_tables);
+    ORIE_CUDA(cudaMemcpyAsync(d_tables, tab.words.data(), tab.words.size() * 4, cudaMemcpyHostToDevice, st));
+    // tab.words stays alive until the end of this function, which ends with a stream synchronisation
 
     // ---- slots, strong insertion slots
-    ORIE_TRY(B.keep(&ix->slot_img, ix->P));
-    ORIE_TRY(B.temp(&slot_tp, ix->P));
-    ORIE_TRY(B.temp(&evcnt, ix->nchunks));
-    ORIE_TRY(B.keep(&ix->evbits, ix->nchunks));
-    ORIE_TRY(B.keep(&ix->evbase, ix->nchunks));
-    ORIE_TRY(B.keep(&ix->seg_ev0, ix->S));
-    fill_u32_kernel<<<grid_for(ix->P), 256, 0, st>>>(ix->slot_img, ix->P, (uint32_t)M);
+    init_slots_kernel<<<148 * 4, 256, 0, st>>>(ix->slot_img, slot_tp, ix->P, ix->lab_slot_img, ix->PL, (uint32_t)M);
     ORIE_LAUNCH_CHECK();
-    ORIE_CUDA(cudaMemsetAsync(slot_tp, 0, (size_t)ix->P * 2, st));
     if (tp_ready) ORIE_CUDA(cudaStreamWaitEvent(st, tp_ready, 0));     // first reader of the true-positive masks
     if (n) {
         place_slots_kernel<<<grid_for(n), 256, 0, st>>>(dets, order, wpre, img_all, n, d_cls_off, d_pad_off, ix->slot_img,
@@ -508,73 +584,40 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     }
 
     // ---- events (the total is read back together with the final synchronisation; evmask is sized by its bound)
-    event_bits_kernel<<<grid_for(ix->nchunks * 32), 256, 0, st>>>(slot_tp, ix->nchunks, ix->evbits, evcnt);
-    ORIE_LAUNCH_CHECK();
-    ORIE_TRY(exclusive_scan_u32(evcnt, ix->evbase, ix->nchunks, d_total, sscratch, st));
-    ORIE_CUDA(cudaMemcpyAsync(&h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
-    ORIE_TRY(B.keep(&ix->evmask, Dw));             // events <= weak detections
-    event_mask_kernel<<<grid_for(ix->nchunks * 32), 256, 0, st>>>(slot_tp, ix->nchunks, ix->evbits, ix->evbase, ix->evmask);
-    ORIE_LAUNCH_CHECK();
-    gather_seg_ev0_kernel<<<grid_for(ix->S), 256, 0, st>>>(ix->seg_chunk0, ix->S, ix->evbase, ix->seg_ev0);
-    ORIE_LAUNCH_CHECK();
+    {
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ev_blocks, ceil_div(ix->nchunks, 4 * (kEvThreads / 32))));
+        int64_t per = ceil_div(std::max<int64_t>(ix->nchunks, 1), blocks);
+        unsigned *bar = (unsigned *)scratch;
+        uint32_t *table = (uint32_t *)(scratch + 256);
+        ORIE_CUDA(cudaMemsetAsync(bar, 0, 4, st));
+        const uint16_t *tp_c = slot_tp;
+        int64_t nch = ix->nchunks, S = ix->S;
+        void *args[] = {&tp_c, &nch, &per, &ix->evbits, &ix->evbase, &ix->evmask, &ix->seg_chunk0, &S, &ix->seg_ev0,
+                        &table, &bar, &d_total};
+        ORIE_CUDA(cudaLaunchCooperativeKernel((const void *)events_kernel, dim3(blocks), dim3(kEvThreads), args, 0, st));
+        ORIE_LAUNCH_CHECK();
+        ORIE_CUDA(cudaMemcpyAsync(&h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
+    }
 
     // ---- own lists (image-major) and batch query lists (batch-major), both detectors in one pass each
-    ORIE_TRY(B.keep(&ix->own_w_q, Dw));
-    ORIE_TRY(B.keep(&ix->own_w_m, Dw));
-    ORIE_TRY(B.keep(&ix->own_s_q, Ds));
-    ORIE_TRY(B.keep(&ix->own_s_m, Ds));
-    ORIE_TRY(B.keep(&ix->own_w_cs, M * (C + 1)));
-    ORIE_TRY(B.keep(&ix->own_s_cs, M * (C + 1)));
-    ORIE_TRY(B.keep(&ix->bq_w, Dw));
-    ORIE_TRY(B.keep(&ix->bq_s, Ds));
-    ORIE_TRY(B.keep(&ix->bqoff_w, ix->nbatch * (ix->S + 1)));
-    ORIE_TRY(B.keep(&ix->bqoff_s, ix->nbatch * (ix->S + 1)));
-    ORIE_CUDA(cudaMemsetAsync(ix->own_w_cs, 0, (size_t)(M * (C + 1)) * 2, st));
-    ORIE_CUDA(cudaMemsetAsync(ix->own_s_cs, 0, (size_t)(M * (C + 1)) * 2, st));
     if (n) {
-        ORIE_CUDA(cudaMemcpyAsync(vals, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-        rekey_kernel<kKeyImageDetector><<<grid_for(n), 256, 0, st>>>(dets, img_all, vals, n, keys);
-        ORIE_LAUNCH_CHECK();
-        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 0, ibits, rscratch, st));
-        own_fill_kernel<<<grid_for(n), 256, 0, st>>>(dets, vals, img_all, n, ix->w_off, ix->s_off, q_of_det, ix->own_w_q,
+        own_fill_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_img, img_all, n, ix->w_off, ix->s_off, q_of_det, ix->own_w_q,
                                                    ix->own_w_m, own_w_c, ix->own_s_q, ix->own_s_m, own_s_c, ownpos);
         ORIE_LAUNCH_CHECK();
-        if (Dw) {
-            own_class_start_kernel<<<grid_for(Dw), 256, 0, st>>>(own_w_c, img_all, Dw, ix->w_off, C, ix->own_w_cs);
-            ORIE_LAUNCH_CHECK();
-        }
-        if (Ds) {
-            own_class_start_kernel<<<grid_for(Ds), 256, 0, st>>>(own_s_c, img_all + Dw, Ds, ix->s_off, C, ix->own_s_cs);
-            ORIE_LAUNCH_CHECK();
-        }
-        ORIE_CUDA(cudaMemcpyAsync(vals, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-        rekey_kernel<kKeyBatchDetector><<<grid_for(n), 256, 0, st>>>(dets, img_all, vals, n, keys);
-        ORIE_LAUNCH_CHECK();
-        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 0, bbits, rscratch, st));
-        batch_query_kernel<<<grid_for(n), 256, 0, st>>>(dets, vals, img_all, n, M, ix->w_off, ix->s_off, q_of_det, ownpos,
+        batch_query_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_bat, img_all, n, M, ix->w_off, ix->s_off, q_of_det, ownpos,
                                                       ix->bq_w, ix->bq_s);
         ORIE_LAUNCH_CHECK();
     }
-    batch_query_offsets_kernel<<<grid_for(ix->nbatch * (ix->S + 1)), 256, 0, st>>>(ix->bq_w, ix->w_off, M, ix->nbatch,
-                                                                                 ix->seg_chunk0, ix->S, ix->bqoff_w);
+    own_class_start_kernel<<<grid_for(2 * M * 32), 256, 0, st>>>(own_w_c, ix->w_off, ix->own_w_cs, own_s_c, ix->s_off,
+                                                               ix->own_s_cs, M, C);
     ORIE_LAUNCH_CHECK();
-    batch_query_offsets_kernel<<<grid_for(ix->nbatch * (ix->S + 1)), 256, 0, st>>>(ix->bq_s, ix->s_off, M, ix->nbatch,
-                                                                                 ix->seg_chunk0, ix->S, ix->bqoff_s);
+    batch_query_offsets_kernel<<<grid_for(2 * ix->nbatch * (ix->S + 1)), 256, 0, st>>>(
+        ix->bq_w, ix->w_off, ix->bqoff_w, ix->bq_s, ix->s_off, ix->bqoff_s, M, ix->nbatch, ix->seg_chunk0, ix->S);
     ORIE_LAUNCH_CHECK();
 
     // ---- label stream
-    ORIE_TRY(B.keep(&ix->lab_slot_img, ix->PL));
-    ORIE_TRY(B.keep(&ix->gtcnt, M * C));
-    ORIE_CUDA(cudaMemsetAsync(ix->gtcnt, 0, (size_t)(M * C) * 4, st));
-    if (ix->PL) {
-        fill_u32_kernel<<<grid_for(ix->PL), 256, 0, st>>>(ix->lab_slot_img, ix->PL, (uint32_t)M);
-        ORIE_LAUNCH_CHECK();
-    }
     if (G) {
-        label_keys_kernel<<<grid_for(G), 256, 0, st>>>(l_cls, img_l, G, C, keys, vals, ix->gtcnt);
-        ORIE_LAUNCH_CHECK();
-        ORIE_TRY(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, G, 0, cbits, rscratch, st));
-        place_labels_kernel<<<grid_for(G), 256, 0, st>>>(keys, vals, G, d_lcls_off, d_lpad_off, ix->lab_slot_img);
+        place_labels_kernel<<<grid_for(G), 256, 0, st>>>(lorder, l_cls, img_l, G, d_lcls_off, d_lpad_off, ix->lab_slot_img);
         ORIE_LAUNCH_CHECK();
     }
     ORIE_CUDA(cudaStreamSynchronize(st));

@@ -218,9 +218,10 @@ class Engine:
         iou_p = self.iouv.ctypes.data_as(C.POINTER(C.c_double))
 
         def run(box, cls, off, n):
-            tp = torch.zeros(max(n, 1), dtype=torch.int16, device=dev)
-            mi = torch.full((max(n, 1),), -1, dtype=torch.int32, device=dev)
-            bi = torch.zeros(max(n, 1), dtype=torch.float64, device=dev)
+            # orie_match writes all three outputs for every row of every image
+            tp = torch.empty(max(n, 1), dtype=torch.int16, device=dev)
+            mi = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            bi = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
             _lib.check(self.lib.orie_match(_ptr(box), _ptr(cls), _ptr(off), _ptr(self.l_box), _ptr(self.l_cls),
                                            _ptr(self.l_off), iou_p, self.T, self.M, _ptr(tp), _ptr(mi), _ptr(bi), st))
             return tp, mi, bi

@@ -40,3 +40,15 @@ for rep in range(6):
     h = r.cpu(); sync(); t.append(time.perf_counter())
     eng.close(); sync(); t.append(time.perf_counter())
     print("e2e ms: h2d %.2f  match+index %.2f  reward %.2f  d2h %.2f  close %.2f" % tuple(1e3 * (b - a) for a, b in zip(t, t[1:])), flush=True)
+
+# pipelined (pinned host -> Engine) breakdown, as bench.py's e2e does it
+for rep in range(6):
+    sync()
+    t = [time.perf_counter()]
+    eng = Engine(hp, iouv=iouv, device=dev); t.append(time.perf_counter())
+    sync(); t.append(time.perf_counter())
+    r = eng.orie_device(N, seed=rep); t.append(time.perf_counter())
+    h = r.cpu(); sync(); t.append(time.perf_counter())
+    eng.close()
+    print("pipelined ms: Engine() returns %.2f  +sync %.2f  orie enqueue %.2f  cpu() %.2f   total %.2f" %
+          (tuple(1e3 * (b - a) for a, b in zip(t, t[1:])) + (1e3 * (t[-1] - t[0]),)), flush=True)
