@@ -1,4 +1,5 @@
-"""Build liborie_b200.so in-tree with nvcc for sm_100a (no other target)."""
+"""Build liborie_b200.so in-tree with nvcc for sm_100a (no other target), and the host-only
+file reader liborie_io.so with g++."""
 from __future__ import annotations
 
 import os
@@ -10,7 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liborie_b200.so")
 SOURCES = ["api.cu", "sort.cu", "match.cu", "index.cu", "reward.cu"]
-HEADERS = ["common.cuh", "index.cuh", os.path.join("..", "..", "include", "orie_b200.h")]
+HEADERS = ["common.cuh", "coop.cuh", "index.cuh", os.path.join("..", "..", "include", "orie_b200.h")]
+IO_LIB = os.path.join(HERE, "liborie_io.so")
+IO_SOURCES = ["loader.cpp"]
+IO_HEADERS = [os.path.join("..", "..", "include", "orie_io.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -51,5 +55,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def io_stale() -> bool:
+    if not os.path.exists(IO_LIB):
+        return True
+    t = os.path.getmtime(IO_LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in IO_SOURCES + IO_HEADERS)
+
+
+def build_io(force: bool = False) -> str:
+    """liborie_io.so: the native reader of the label / detection files (plain C++17 + pthreads, no CUDA)."""
+    if not force and not io_stale():
+        return IO_LIB
+    gxx = shutil.which("g++") or shutil.which("c++")
+    if gxx is None:
+        raise RuntimeError("g++ not found; liborie_io.so cannot be built")
+    cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-pthread"] + \
+          [os.path.join(CSRC, f) for f in IO_SOURCES] + ["-o", IO_LIB]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return IO_LIB
+
+
 if __name__ == "__main__":
+    print(build_io(force="--force" in sys.argv))
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

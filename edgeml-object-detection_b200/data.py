@@ -45,33 +45,66 @@ def _parse_text(path: str) -> np.ndarray:
     return np.array([r[:width] for r in table]).astype(float).reshape(len(table), width)
 
 
-def read_rows(path: str, names, with_conf: bool) -> Rows:
-    """Rows of every image in ``names`` from directory ``path`` as one CSR
-    block: labels -> ``cls xc yc w h``; detections -> ``cls xc yc w h conf``."""
+def _read_image(stem: str, need: int, with_conf: bool):
+    """Rows of one image, the way ``lib/data.py:23-38`` reads them (``.txt`` first, else ``.npy``, else none)."""
+    arr = None
+    if os.path.isfile(stem + ".txt"):
+        arr = _parse_text(stem + ".txt")
+    elif os.path.isfile(stem + ".npy"):
+        arr = np.asarray(np.load(stem + ".npy"), dtype=float)
+        if arr.ndim != 2:
+            arr = arr.reshape(len(arr), -1) if arr.size else np.zeros((0, 0))
+    if arr is None or len(arr) == 0:
+        return None
+    if arr.shape[1] < need:
+        raise ValueError(f"{stem}: expected at least {need} columns per row, found {arr.shape[1]}")
+    if with_conf:
+        return np.concatenate([arr[:, 0:5], arr[:, -1:]], axis=1)
+    return arr[:, 0:5]
+
+
+def read_rows_python(path: str, names, with_conf: bool) -> Rows:
+    """Pure-Python reader: the reference-equivalent statement of ``lib/data.py:11-43`` (one file at a time)."""
     need = 6 if with_conf else 5
     blocks, counts = [], []
     for name in names:
-        stem = os.path.join(path, name)
-        arr = None
-        if os.path.isfile(stem + ".txt"):
-            arr = _parse_text(stem + ".txt")
-        elif os.path.isfile(stem + ".npy"):
-            arr = np.asarray(np.load(stem + ".npy"), dtype=float)
-            if arr.ndim != 2:
-                arr = arr.reshape(len(arr), -1) if arr.size else np.zeros((0, 0))
-        if arr is None or len(arr) == 0:
+        arr = _read_image(os.path.join(path, name), need, with_conf)
+        if arr is None:
             counts.append(0)
             continue
-        if arr.shape[1] < need:
-            raise ValueError(f"{stem}: expected at least {need} columns per row, found {arr.shape[1]}")
-        if with_conf:
-            arr = np.concatenate([arr[:, 0:5], arr[:, -1:]], axis=1)
-        else:
-            arr = arr[:, 0:5]
         blocks.append(arr)
         counts.append(len(arr))
     rows = np.concatenate(blocks, axis=0) if blocks else np.zeros((0, need))
     off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return Rows(off, np.ascontiguousarray(rows, dtype=np.float64))
+
+
+def read_rows(path: str, names, with_conf: bool, native: bool = True, threads: int = 0) -> Rows:
+    """Rows of every image in ``names`` from directory ``path`` as one CSR
+    block: labels -> ``cls xc yc w h``; detections -> ``cls xc yc w h conf``.
+
+    ``native=True`` (default) reads with the multi-threaded C++ reader (``csrc/loader.cpp`` through
+    ``include/orie_io.h``); the few files it hands back (anything that is not plain numeric text or a little-endian
+    f4/f8 ``.npy`` matrix) are re-read by the Python path, which raises what the reference raises."""
+    if not native:
+        return read_rows_python(path, names, with_conf)
+    from . import _io
+    need = 6 if with_conf else 5
+    off, rows, fallback = _io.read_rows(path, list(names), with_conf, threads)
+    if len(fallback):
+        extra = {int(i): _read_image(os.path.join(path, names[int(i)]), need, with_conf) for i in fallback}
+        extra = {i: a for i, a in extra.items() if a is not None}
+        if extra:
+            counts = np.diff(off)
+            blocks, prev = [], 0
+            for i in sorted(extra):
+                blocks.append(rows[off[prev]:off[i]])
+                blocks.append(np.ascontiguousarray(extra[i], dtype=np.float64))
+                counts[i] = len(extra[i])
+                prev = i
+            blocks.append(rows[off[prev]:])
+            rows = np.concatenate(blocks, axis=0)
+            off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     return Rows(off, np.ascontiguousarray(rows, dtype=np.float64))
 
 
