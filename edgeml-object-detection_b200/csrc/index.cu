@@ -120,14 +120,13 @@ __global__ void place_slots_kernel(const Dets d, const uint32_t *__restrict__ or
     }
 }
 
-// ---- event table in one cooperative launch: per chunk the slots holding a true positive (evbits), the
-// chunk's first event (evbase = exclusive scan of the counts), the compacted masks (evmask), the total,
-// and each segment's first event.
+// ---- event counts in one cooperative launch: events (slots holding a true positive) in front of every chunk
+// (evbase = exclusive scan of the per-chunk counts), their total, and each segment's first event.
 constexpr int kEvThreads = 512;
 __global__ void __launch_bounds__(kEvThreads)
-events_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks, int64_t per, uint32_t *__restrict__ evbits,
-              uint32_t *evbase, uint16_t *__restrict__ evmask, const int32_t *__restrict__ seg_chunk0, int64_t S,
-              uint32_t *__restrict__ seg_ev0, uint32_t *table, unsigned *bar, uint32_t *__restrict__ total_out) {
+events_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks, int64_t per, uint32_t *evbase,
+              const int32_t *__restrict__ seg_chunk0, int64_t S, uint32_t *__restrict__ seg_ev0, uint32_t *table,
+              unsigned *bar, uint32_t *__restrict__ total_out) {
     __shared__ uint32_t ws[kEvThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned epoch = 0;
@@ -136,9 +135,7 @@ events_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks, int64_t per
     const int64_t w0 = c0 + warp * cw, w1 = w0 + cw < c1 ? w0 + cw : c1;
     uint32_t mine = 0;
     for (int64_t ch = w0; ch < w1; ++ch) {
-        const unsigned b = __ballot_sync(kFull, slot_tp[ch * 32 + lane] != 0);
-        if (lane == 0) evbits[ch] = b;
-        mine += __popc(b);
+        mine += __popc(__ballot_sync(kFull, slot_tp[ch * 32 + lane] != 0));
     }
     uint32_t cta_total;
     const uint32_t excl = block_exclusive_scan<kEvThreads>(lane == 0 ? mine : 0u, ws, &cta_total);
@@ -157,10 +154,8 @@ events_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks, int64_t per
     if (blockIdx.x == 0 && threadIdx.x == 0) *total_out = grand;
     uint32_t run = carry + warp_base;
     for (int64_t ch = w0; ch < w1; ++ch) {
-        const uint16_t tp = slot_tp[ch * 32 + lane];
-        const unsigned b = __ballot_sync(kFull, tp != 0);
+        const unsigned b = __ballot_sync(kFull, slot_tp[ch * 32 + lane] != 0);
         if (lane == 0) evbase[ch] = run;
-        if (tp) evmask[run + __popc(b & ((1u << lane) - 1u))] = tp;
         run += __popc(b);
     }
     grid_sync(bar, epoch);
@@ -168,28 +163,24 @@ events_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks, int64_t per
         seg_ev0[s] = __ldcg(evbase + seg_chunk0[s]);
 }
 
-// Image-major order (sorted by image * 2 + is_strong, stable on the (class, conf) order): image i occupies
-// [w_off[i] + s_off[i], ...), its weak rows first.  Fills the own lists (aligned with w_off / s_off) and
-// remembers each row's own position.
-__global__ void own_fill_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ img_all,
-                                int64_t n, const int64_t *__restrict__ w_off, const int64_t *__restrict__ s_off,
-                                const uint32_t *__restrict__ q_of_det, uint32_t *__restrict__ own_w_q,
+// Image-major order (the (class, conf) order stably regrouped by image; weak and strong rows of an image stay
+// interleaved).  wrank[v] = weak rows in front of position v, so the weak row at v is entry wrank[v] of the weak own
+// lists (which are aligned with w_off) and the strong row at v is entry v - wrank[v] of the strong ones.
+__global__ void own_fill_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ wrank,
+                                int64_t n, const uint32_t *__restrict__ q_of_det, uint32_t *__restrict__ own_w_q,
                                 uint16_t *__restrict__ own_w_m, uint16_t *__restrict__ own_w_c, uint32_t *__restrict__ own_s_q,
                                 uint16_t *__restrict__ own_s_m, uint16_t *__restrict__ own_s_c, uint32_t *__restrict__ ownpos) {
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const uint32_t u = order[v];
-    const uint32_t im = img_all[u];
-    const int64_t local = v - (w_off[im] + s_off[im]);
-    const int64_t nw = w_off[im + 1] - w_off[im];
     if (u < d.Dw) {
-        const int64_t pos = w_off[im] + local;
+        const uint32_t pos = wrank[v];
         own_w_q[pos] = q_of_det[u]; own_w_m[pos] = d.w_tp[u]; own_w_c[pos] = (uint16_t)d.w_cls[u];
-        ownpos[u] = (uint32_t)pos;
+        ownpos[u] = pos;
     } else {
-        const int64_t pos = s_off[im] + (local - nw);
+        const uint32_t pos = (uint32_t)v - wrank[v];
         own_s_q[pos] = q_of_det[u]; own_s_m[pos] = d.s_tp[u - d.Dw]; own_s_c[pos] = (uint16_t)d.s_cls[u - d.Dw];
-        ownpos[u] = (uint32_t)pos;
+        ownpos[u] = pos;
     }
 }
 
@@ -217,23 +208,17 @@ __global__ void own_class_start_kernel(const uint16_t *__restrict__ own_w_c, con
     }
 }
 
-// Batch-major order (sorted by (image / 32) * 2 + is_strong): batch b occupies [w_off[32b] + s_off[32b], ...),
-// its weak rows first, each part ascending by query slot.
-__global__ void batch_query_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ img_all,
-                                   int64_t n, int64_t M, const int64_t *__restrict__ w_off, const int64_t *__restrict__ s_off,
-                                   const uint32_t *__restrict__ q_of_det, const uint32_t *__restrict__ ownpos,
-                                   uint2 *__restrict__ bq_w, uint2 *__restrict__ bq_s) {
+// Batch-major order (the (class, conf) order stably regrouped by 32-image batch): the weak rows of a batch, ascending
+// by query slot, are the entries [w_off[32b], w_off[32b + 32]) of bq_w — again addressed by the weak rank.
+__global__ void batch_query_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ wrank,
+                                   const uint32_t *__restrict__ img_all, int64_t n, const uint32_t *__restrict__ q_of_det,
+                                   const uint32_t *__restrict__ ownpos, uint2 *__restrict__ bq_w, uint2 *__restrict__ bq_s) {
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const uint32_t u = order[v];
-    const uint32_t im = img_all[u];
-    const int64_t i0 = (int64_t)(im >> 5) * 32;
-    const int64_t i1 = i0 + 32 < M ? i0 + 32 : M;
-    const int64_t local = v - (w_off[i0] + s_off[i0]);
-    const int64_t nw = w_off[i1] - w_off[i0];
-    const uint2 e = make_uint2(q_of_det[u], ((im & 31u) << 27) | ownpos[u]);
-    if (u < d.Dw) bq_w[w_off[i0] + local] = e;
-    else bq_s[s_off[i0] + (local - nw)] = e;
+    const uint2 e = make_uint2(q_of_det[u], ((img_all[u] & 31u) << 27) | ownpos[u]);
+    if (u < d.Dw) bq_w[wrank[v]] = e;
+    else bq_s[(uint32_t)v - wrank[v]] = e;
 }
 
 // bqoff[b][s] = first entry of batch b with q >= first slot of segment s  (s == S: end of the batch); both detectors
@@ -429,12 +414,11 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&ix->own_s_cs, M * (C + 1));
     A.add(&ix->bq_w, Dw);
     A.add(&ix->bq_s, Ds);
-    A.add(&ix->evmask, Dw);              // events <= weak detections
     A.add(&ix->gtcnt, M * C);
     ORIE_TRY(B.keep(A));
 
     uint64_t *keys, *keys_tmp;
-    uint32_t *vtmp, *img_all, *img_l, *order, *ord_img, *ord_bat, *lorder, *meta, *wpre, *q_of_det, *ownpos, *d_total;
+    uint32_t *vtmp, *img_all, *img_l, *order, *ord_img, *ord_bat, *rank_img, *rank_bat, *lorder, *meta, *wpre, *q_of_det, *ownpos, *d_total;
     uint16_t *own_w_c, *own_s_c;
     char *scratch;
     A.add(&keys, n);
@@ -445,6 +429,8 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&order, n);
     A.add(&ord_img, n);
     A.add(&ord_bat, n);
+    A.add(&rank_img, n);
+    A.add(&rank_bat, n);
     A.add(&lorder, G);
     A.add(&meta, 3 * C + 1);
     A.add(&wpre, n);
@@ -462,7 +448,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     ORIE_CUDA(cudaMemsetAsync(meta, 0, (size_t)(3 * C + 1) * 4, st));
     ORIE_CUDA(cudaMemsetAsync(ix->gtcnt, 0, (size_t)(M * C) * 4, st));
 
-    const int cbits = bits_for(C), ibits = bits_for(M) + 1, bbits = bits_for(ix->nbatch) + 1;
+    const int cbits = bits_for(C), ibits = bits_for(M), bbits = bits_for(ix->nbatch);
 
     // ---- prep: images of rows, confidence keys, class histograms, ground-truth counts, validation
     {
@@ -486,16 +472,19 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         ORIE_TRY(sort_add_passes(&j, kDigitKey, 0, 64));
         ORIE_TRY(sort_add_passes(&j, kDigitClass, 0, cbits));
         ORIE_TRY(sort_run(j, sort_blocks, scratch, st));
-        // the same order regrouped by image and by 32-image batch (both detectors at once, weak first)
+        // the same order regrouped by image and by 32-image batch (both detectors at once); the rank epilogue
+        // separates weak from strong rows, which saves the detector bit of the key (one pass at COCO scale)
         SortJob r;
         r.n = n;
         r.vals_in = order; r.vals_a = ord_img; r.vals_b = vtmp;
-        r.img = img_all; r.split = (uint32_t)Dw;
-        ORIE_TRY(sort_add_passes(&r, kDigitImageDetector, 0, ibits));
+        r.img = img_all;
+        r.rank_out = rank_img; r.rank_split = (uint32_t)Dw;
+        ORIE_TRY(sort_add_passes(&r, kDigitImage, 0, ibits));
         ORIE_TRY(sort_run(r, sort_blocks, scratch, st));
         r.npass = 0;
         r.vals_a = ord_bat;
-        ORIE_TRY(sort_add_passes(&r, kDigitBatchDetector, 0, bbits));
+        r.rank_out = rank_bat;
+        ORIE_TRY(sort_add_passes(&r, kDigitBatch, 0, bbits));
         ORIE_TRY(sort_run(r, sort_blocks, scratch, st));
     }
     if (G) {
@@ -558,42 +547,39 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     tab.add(&ix->lcls_seg0, LL.cls_seg0);
 
     // ---- second part of the index (sizes depend on the class counts)
-    uint16_t *slot_tp;
     A.add(&d_tables, (int64_t)tab.words.size());
     A.add(&ix->slot_img, ix->P);
-    A.add(&ix->evbits, ix->nchunks);
+    A.add(&ix->slot_tp, ix->P);
     A.add(&ix->evbase, ix->nchunks);
     A.add(&ix->seg_ev0, ix->S);
     A.add(&ix->bqoff_w, ix->nbatch * (ix->S + 1));
     A.add(&ix->bqoff_s, ix->nbatch * (ix->S + 1));
     A.add(&ix->lab_slot_img, ix->PL);
-    A.add(&slot_tp, ix->P);              // only needed during the build; rides along (2 bytes per slot)
     ORIE_TRY(B.keep(A));
     tab.bind(d_tables);
     ORIE_CUDA(cudaMemcpyAsync(d_tables, tab.words.data(), tab.words.size() * 4, cudaMemcpyHostToDevice, st));
     // tab.words stays alive until the end of this function, which ends with a stream synchronisation
 
     // ---- slots, strong insertion slots
-    init_slots_kernel<<<148 * 4, 256, 0, st>>>(ix->slot_img, slot_tp, ix->P, ix->lab_slot_img, ix->PL, (uint32_t)M);
+    init_slots_kernel<<<148 * 4, 256, 0, st>>>(ix->slot_img, ix->slot_tp, ix->P, ix->lab_slot_img, ix->PL, (uint32_t)M);
     ORIE_LAUNCH_CHECK();
     if (tp_ready) ORIE_CUDA(cudaStreamWaitEvent(st, tp_ready, 0));     // first reader of the true-positive masks
     if (n) {
         place_slots_kernel<<<grid_for(n), 256, 0, st>>>(dets, order, wpre, img_all, n, d_cls_off, d_pad_off, ix->slot_img,
-                                                      slot_tp, q_of_det);
+                                                      ix->slot_tp, q_of_det);
         ORIE_LAUNCH_CHECK();
     }
 
-    // ---- events (the total is read back together with the final synchronisation; evmask is sized by its bound)
+    // ---- events (the total is read back together with the final synchronisation)
     {
         const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ev_blocks, ceil_div(ix->nchunks, 4 * (kEvThreads / 32))));
         int64_t per = ceil_div(std::max<int64_t>(ix->nchunks, 1), blocks);
         unsigned *bar = (unsigned *)scratch;
         uint32_t *table = (uint32_t *)(scratch + 256);
         ORIE_CUDA(cudaMemsetAsync(bar, 0, 4, st));
-        const uint16_t *tp_c = slot_tp;
+        const uint16_t *tp_c = ix->slot_tp;
         int64_t nch = ix->nchunks, S = ix->S;
-        void *args[] = {&tp_c, &nch, &per, &ix->evbits, &ix->evbase, &ix->evmask, &ix->seg_chunk0, &S, &ix->seg_ev0,
-                        &table, &bar, &d_total};
+        void *args[] = {&tp_c, &nch, &per, &ix->evbase, &ix->seg_chunk0, &S, &ix->seg_ev0, &table, &bar, &d_total};
         ORIE_CUDA(cudaLaunchCooperativeKernel((const void *)events_kernel, dim3(blocks), dim3(kEvThreads), args, 0, st));
         ORIE_LAUNCH_CHECK();
         ORIE_CUDA(cudaMemcpyAsync(&h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
@@ -601,11 +587,10 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
 
     // ---- own lists (image-major) and batch query lists (batch-major), both detectors in one pass each
     if (n) {
-        own_fill_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_img, img_all, n, ix->w_off, ix->s_off, q_of_det, ix->own_w_q,
-                                                   ix->own_w_m, own_w_c, ix->own_s_q, ix->own_s_m, own_s_c, ownpos);
+        own_fill_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_img, rank_img, n, q_of_det, ix->own_w_q, ix->own_w_m, own_w_c,
+                                                   ix->own_s_q, ix->own_s_m, own_s_c, ownpos);
         ORIE_LAUNCH_CHECK();
-        batch_query_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_bat, img_all, n, M, ix->w_off, ix->s_off, q_of_det, ownpos,
-                                                      ix->bq_w, ix->bq_s);
+        batch_query_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_bat, rank_bat, img_all, n, q_of_det, ownpos, ix->bq_w, ix->bq_s);
         ORIE_LAUNCH_CHECK();
     }
     own_class_start_kernel<<<grid_for(2 * M * 32), 256, 0, st>>>(own_w_c, ix->w_off, ix->own_w_cs, own_s_c, ix->s_off,

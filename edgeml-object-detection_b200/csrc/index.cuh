@@ -14,9 +14,8 @@ struct orie_index {
     //      to a whole number of 32-slot chunks with at least one padding slot
     int64_t P = 0, nchunks = 0, S = 0, Ev = 0;
     uint32_t *slot_img = nullptr;    // [P] image of the detection in the slot (M for padding)
-    uint32_t *evbits = nullptr;      // [nchunks] slots holding a detection that is a TP at >= 1 threshold
-    uint32_t *evbase = nullptr;      // [nchunks] index of the chunk's first event in evmask
-    uint16_t *evmask = nullptr;      // [Ev] TP mask of each event
+    uint16_t *slot_tp = nullptr;     // [P] its true-positive mask (0 for padding); non-zero = "event"
+    uint32_t *evbase = nullptr;      // [nchunks] number of events in front of the chunk
     int32_t *seg_chunk0 = nullptr;   // [S]
     int32_t *seg_nch = nullptr;      // [S]
     uint32_t *seg_ev0 = nullptr;     // [S] evbase[seg_chunk0[s]]

@@ -10,8 +10,9 @@
 //   d is a TP at threshold t  <=>  IoU[best[d], d] >= t and no earlier row d' < d
 //             of the same image has best[d'] == best[d] with IoU >= t.
 // One CTA per (image, detector).  Label boxes are staged in shared memory with
-// 16-byte loads; "first detection per label" is a shared-memory atomicMin issued
-// by the lowest lane of each __match_any_sync peer group.
+// 16-byte loads; "first detection per label" is a shared-memory atomicMin — for all
+// thresholds in one pass when labels x thresholds fit the table (the usual case),
+// otherwise per threshold, issued by the lowest lane of each __match_any_sync group.
 // All IoU arithmetic is IEEE float64 in upstream's operation order; the library
 // is compiled with -fmad=false so nothing is contracted into an FMA.
 #include "common.cuh"
@@ -37,12 +38,13 @@ __device__ __forceinline__ double iou_f64(double lx1, double ly1, double lx2, do
 __global__ void __launch_bounds__(kMatchThreads)
 match_kernel(const double *__restrict__ det_box, const int32_t *__restrict__ det_cls, const int64_t *__restrict__ det_off,
              const double *__restrict__ lab_box, const int32_t *__restrict__ lab_cls, const int64_t *__restrict__ lab_off,
-             Thresholds thr, int T, uint16_t *__restrict__ tp_mask, int32_t *__restrict__ match_idx,
+             const __grid_constant__ Thresholds thr, int T, uint16_t *__restrict__ tp_mask, int32_t *__restrict__ match_idx,
              double *__restrict__ best_iou) {
     __shared__ double2 s_box[kLabTile][2];   // (x1,y1),(x2,y2)
     __shared__ double s_area[kLabTile];
     __shared__ int32_t s_cls[kLabTile];
     __shared__ int32_t s_first[kFirstCap];
+    __shared__ double s_thr[ORIE_MAX_THRESHOLDS];
 
     const int64_t img = blockIdx.x;
     const int64_t d0 = det_off[img];
@@ -51,6 +53,7 @@ match_kernel(const double *__restrict__ det_box, const int32_t *__restrict__ det
     const int nl = (int)(lab_off[img + 1] - l0);
     if (nd == 0) return;
     const int tid = threadIdx.x;
+    if (tid < ORIE_MAX_THRESHOLDS) s_thr[tid] = thr.v[tid];      // read again only after a __syncthreads
     if (nl == 0) {
         for (int d = tid; d < nd; d += kMatchThreads) {
             tp_mask[d0 + d] = 0;
@@ -108,9 +111,32 @@ match_kernel(const double *__restrict__ det_box, const int32_t *__restrict__ det
 
     // ---- phase 2: first (lowest row) candidate per label and threshold
     const int lane = tid & 31;
-    if (nl <= kFirstCap) {
+    if (nl * T <= kFirstCap) {
+        // all thresholds in one pass: first[t][label] = lowest row that claims the label at threshold t
+        for (int i = tid; i < nl * T; i += kMatchThreads) s_first[i] = 0x7fffffff;
+        __syncthreads();
+        for (int d = tid; d < nd; d += kMatchThreads) {
+            const int best = match_idx[d0 + d];
+            if (best < 0) continue;
+            const double bv = best_iou[d0 + d];
+            for (int t = 0; t < T; ++t)
+                if (bv >= s_thr[t]) atomicMin(&s_first[t * nl + best], d);
+        }
+        __syncthreads();
+        for (int d = tid; d < nd; d += kMatchThreads) {
+            const int best = match_idx[d0 + d];
+            unsigned mask = 0;
+            if (best >= 0) {
+                const double bv = best_iou[d0 + d];
+                for (int t = 0; t < T; ++t)
+                    if (bv >= s_thr[t] && s_first[t * nl + best] == d) mask |= 1u << t;
+            }
+            tp_mask[d0 + d] = (uint16_t)mask;
+            if (mask == 0) match_idx[d0 + d] = -1;
+        }
+    } else if (nl <= kFirstCap) {
         for (int t = 0; t < T; ++t) {
-            const double th = thr.v[t];
+            const double th = s_thr[t];
             __syncthreads();
             for (int i = tid; i < nl; i += kMatchThreads) s_first[i] = 0x7fffffff;
             __syncthreads();
@@ -140,10 +166,10 @@ match_kernel(const double *__restrict__ det_box, const int32_t *__restrict__ det
             unsigned mask = 0;
             if (best >= 0) {
                 for (int t = 0; t < T; ++t) {
-                    if (!(bv >= thr.v[t])) continue;
+                    if (!(bv >= s_thr[t])) continue;
                     bool first = true;
                     for (int e = 0; e < d && first; ++e)
-                        if (match_idx[d0 + e] == best && best_iou[d0 + e] >= thr.v[t]) first = false;
+                        if (match_idx[d0 + e] == best && best_iou[d0 + e] >= s_thr[t]) first = false;
                     if (first) mask |= 1u << t;
                 }
             }

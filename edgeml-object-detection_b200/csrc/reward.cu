@@ -81,9 +81,13 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     return ctr;
 }
 
-// One warp per target.  Draws `want` distinct images != target into the target's bitmap
-// (32 candidates per round, duplicates inside a round resolved by lane order, quota cut in lane
-// order), then complements the bitmap when the ensemble is more than half of the dataset.
+// One warp per target.  Draws `want` distinct images != target into the target's bitmap, then complements the
+// bitmap when the ensemble is more than half of the dataset.  Every Philox call yields four 32-bit words per lane,
+// each mapped to [0, M-1) without bias (multiply-shift with rejection, Lemire 2019), i.e. 128 candidates per round.
+//  * bulk rounds (the quota cannot be reached inside the round): every candidate is inserted with an atomic
+//    test-and-set; the SET of accepted images and their count do not depend on the order of the atomics;
+//  * last rounds: 32 candidates at a time, duplicates resolved and the quota cut in lane order, so the result is
+//    a deterministic function of (seed, target).
 // The bitmap is built in shared memory (SMEM = true, one row per warp) or directly in global memory.
 constexpr int kSampleWarps = 4;
 template <bool SMEM>
@@ -101,25 +105,49 @@ ens_sample_kernel(int64_t nt, int64_t N, int64_t t0, int64_t M, int64_t words, u
         for (int64_t w = lane; w < words; w += 32) bits[w] = 0u;
         __syncwarp();
     }
-    const int64_t others = M - 1;
-    const bool complement = 2 * N > others;
-    const int64_t want = complement ? others - N : N;
+    const uint32_t others = (uint32_t)(M - 1);                 // M < 2^27
+    const bool complement = 2 * N > (int64_t)others;
+    const int64_t want = complement ? (int64_t)others - N : N;
+    const uint32_t reject_below = others ? (0u - others) % others : 0u;   // 2^32 mod others
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    // candidate of one random word: image index, or -1 if the word falls in the rejection zone
+    auto candidate = [&](uint32_t rnd) -> int {
+        const uint64_t m = (uint64_t)rnd * others;
+        if ((uint32_t)m < reject_below) return -1;
+        const uint32_t e = (uint32_t)(m >> 32);
+        return (int)(e + (e >= (uint32_t)target ? 1u : 0u));
+    };
     int64_t have = 0;
     for (uint32_t round = 0; have < want; ++round) {
         const uint4 rnd = philox4x32(make_uint4((uint32_t)target, (uint32_t)(target >> 32), round, (uint32_t)lane), key);
-        const uint64_t r64 = ((uint64_t)rnd.x << 32) | rnd.y;
-        int64_t e = (int64_t)__umul64hi(r64, (uint64_t)others);   // uniform in [0, others)
-        e += (e >= target);
-        const unsigned peers = __match_any_sync(kFull, e);
-        bool ok = lane == (__ffs(peers) - 1);
-        const uint32_t bit = 1u << (e & 31);
-        if (ok) ok = !(*(volatile uint32_t *)&bits[e >> 5] & bit);
-        const unsigned acc = __ballot_sync(kFull, ok);
-        const int before = __popc(acc & ((1u << lane) - 1u));
-        if (ok && have + before < want) atomicOr(&bits[e >> 5], bit);
-        __syncwarp();
-        have += __popc(acc);
+        const uint32_t word[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+        if (have + 128 <= want) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = candidate(word[j]);
+                bool fresh = false;
+                if (e >= 0) {
+                    const uint32_t bit = 1u << (e & 31);
+                    fresh = !(atomicOr(&bits[e >> 5], bit) & bit);
+                }
+                have += __popc(__ballot_sync(kFull, fresh));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (have >= want) break;                       // uniform
+                const int e = candidate(word[j]);
+                const unsigned peers = __match_any_sync(kFull, e);
+                bool ok = e >= 0 && lane == (__ffs(peers) - 1);
+                const uint32_t bit = 1u << (e & 31);
+                if (ok) ok = !(*(volatile uint32_t *)&bits[e >> 5] & bit);
+                const unsigned acc = __ballot_sync(kFull, ok);
+                const int before = __popc(acc & ((1u << lane) - 1u));
+                if (ok && have + before < want) atomicOr(&bits[e >> 5], bit);
+                __syncwarp();
+                have += __popc(acc);
+            }
+        }
     }
     __syncwarp();
     for (int64_t w = lane; w < words; w += 32) {
@@ -149,8 +177,7 @@ struct WalkParams {
     int segs_per_block;
     uint32_t *tot;              // [S][ntp]
     // detection stream only
-    const uint32_t *evbits;
-    const uint16_t *evmask;
+    const uint16_t *slot_tp;
     const uint32_t *seg_ev0;
     const uint2 *bq_w, *bq_s;
     const uint32_t *bqoff_w, *bqoff_s;   // [nbatch][S+1]
@@ -206,12 +233,11 @@ walk_kernel(const WalkParams p) {
         const int64_t ch0 = p.seg_chunk0[s];
         const int nch = p.seg_nch[s];
         uint32_t cnt = 0, ecur = 0;
-        uint32_t ev_i = 0, qw = 0, qw_end = 0, qs = 0, qs_end = 0;
+        uint32_t qw = 0, qw_end = 0, qs = 0, qs_end = 0;
         uint2 nqw = make_uint2(0xffffffffu, 0u), nqs = make_uint2(0xffffffffu, 0u);
         uint64_t *evout = nullptr;
         if (DETS) {
-            ev_i = p.seg_ev0[s];
-            evout = p.ev + tl * p.Ev + ev_i;
+            evout = p.ev + tl * p.Ev + p.seg_ev0[s];
             const uint32_t *ow = p.bqoff_w + gb * (p.S + 1) + s;
             const uint32_t *os = p.bqoff_s + gb * (p.S + 1) + s;
             qw = ow[0]; qw_end = ow[1];
@@ -220,30 +246,28 @@ walk_kernel(const WalkParams p) {
             if (qs < qs_end) nqs = p.bq_s[qs];
         }
         const uint32_t *simg = p.slot_img + ch0 * 32 + lane;
-        uint32_t img_next = simg[0];               // software pipeline: the next chunk's images are in flight
-        uint32_t ebv = 0;                          // event bits of 32 chunks, one per lane
+        const uint16_t *stp = DETS ? p.slot_tp + ch0 * 32 + lane : nullptr;
+        uint32_t img_next = simg[0];               // software pipeline: the next chunk's images and masks are in flight
+        uint32_t tp_next = DETS ? (uint32_t)stp[0] : 0u;
         for (int c = 0; c < nch; ++c) {
             const uint32_t img = img_next;
-            if (c + 1 < nch) img_next = simg[(int64_t)(c + 1) * 32];
-            uint32_t eb = 0, mymask = 0;
-            if (DETS) {
-                if ((c & 31) == 0) ebv = (c + lane < nch) ? p.evbits[ch0 + c + lane] : 0u;
-                eb = __shfl_sync(kFull, ebv, c & 31);
-                if (lane < __popc(eb)) mymask = p.evmask[ev_i + lane];   // this chunk's event masks, one per lane
+            const uint32_t tp = tp_next;           // true-positive mask of MY slot of the chunk
+            if (c + 1 < nch) {
+                img_next = simg[(int64_t)(c + 1) * 32];
+                if (DETS) tp_next = stp[(int64_t)(c + 1) * 32];
             }
             const uint32_t word = transpose(GMEM ? __ldg(memb + img) : memb[img]);   // bit l: slot l holds a member of MY target
             if (DETS) {
-                int e = 0;
+                uint32_t eb = __ballot_sync(kFull, tp != 0u);       // slots of the chunk holding an event
                 while (eb) {
                     const int b = __ffs(eb) - 1;
                     eb &= eb - 1;
-                    const uint32_t mask = __shfl_sync(kFull, mymask, e++);
+                    const uint32_t mask = __shfl_sync(kFull, tp, b);
                     if ((word >> b) & 1u) {
                         const uint32_t rank = cnt + __popc(word & ((2u << b) - 1u));   // 1-based, inclusive
                         evout[ecur++] = (uint64_t)rank | ((uint64_t)mask << 32);
                     }
                 }
-                ev_i += e;
                 const uint32_t chunk_end = (uint32_t)(ch0 + c + 1) * 32u;
                 while (nqw.x < chunk_end) {                     // uniform: own weak detections in this chunk
                     if (lane == (int)(nqw.y >> 27))
@@ -432,9 +456,14 @@ ap_kernel(const ApParams p, const Grid101 grid) {
             uint32_t n_ens = 0, K_ens = 0;
             for (int s = s0; s < s1; ++s) {
                 n_ens += tot[(int64_t)s * p.ntp];
-                const uint64_t *e = ev + p.seg_ev0[s];
+                const uint32_t *eh = reinterpret_cast<const uint32_t *>(ev + p.seg_ev0[s]) + 1;   // mask halves of the records
                 const int ne = (int)evcnt[(int64_t)s * p.ntp];
-                for (int i = 0; i < ne; ++i) K_ens += (uint32_t)((e[i] >> (32 + t)) & 1ull);
+                int i = 0;
+                for (; i + 4 <= ne; i += 4) {           // four independent loads in flight
+                    const uint32_t a = eh[2 * i], b = eh[2 * i + 2], c2 = eh[2 * i + 4], d = eh[2 * i + 6];
+                    K_ens += ((a >> t) & 1u) + ((b >> t) & 1u) + ((c2 >> t) & 1u) + ((d >> t) & 1u);
+                }
+                for (; i < ne; ++i) K_ens += (eh[2 * i] >> t) & 1u;
             }
             const uint16_t *wcs = p.own_w_cs + j * (p.C + 1) + c, *scs = p.own_s_cs + j * (p.C + 1) + c;
             const int wa = wcs[0], wb = wcs[1], sa = scs[0], sb = scs[1];
@@ -691,7 +720,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         wp.slot_img = ix->slot_img; wp.seg_chunk0 = ix->seg_chunk0; wp.seg_nch = ix->seg_nch;
         wp.S = ix->S; wp.segs_per_block = segs_per_block(ix->S);
         wp.tot = (uint32_t *)(ws + L.tot);
-        wp.evbits = ix->evbits; wp.evmask = ix->evmask; wp.seg_ev0 = ix->seg_ev0;
+        wp.slot_tp = ix->slot_tp; wp.seg_ev0 = ix->seg_ev0;
         wp.bq_w = ix->bq_w; wp.bq_s = ix->bq_s; wp.bqoff_w = ix->bqoff_w; wp.bqoff_s = ix->bqoff_s;
         wp.Ev = ix->Ev;
         wp.evcnt = (uint32_t *)(ws + L.evcnt);

@@ -39,10 +39,10 @@ __device__ __forceinline__ uint32_t digit_source(const SortJob &j, int kind, uin
     switch (kind) {
     case kDigitClass:
         return (uint32_t)(u < j.split ? __ldg(j.cls_lo + u) : __ldg(j.cls_hi + (u - j.split)));
-    case kDigitImageDetector:
-        return (__ldg(j.img + u) << 1) | (u >= j.split ? 1u : 0u);
-    default:  // kDigitBatchDetector
-        return ((__ldg(j.img + u) >> 5) << 1) | (u >= j.split ? 1u : 0u);
+    case kDigitImage:
+        return __ldg(j.img + u);
+    default:  // kDigitBatch
+        return __ldg(j.img + u) >> 5;
     }
 }
 

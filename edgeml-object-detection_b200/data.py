@@ -158,8 +158,13 @@ def pack(labels: Rows, weak: Rows, strong: Rows) -> Packed:
     if len(values) == 0:
         values = np.zeros(1, dtype=np.int64)
 
+    lut = None
+    if values[0] >= 0 and values[-1] < (1 << 20):        # the usual case: small non-negative class ids
+        lut = np.zeros(int(values[-1]) + 1, dtype=np.int32)
+        lut[values] = np.arange(len(values), dtype=np.int32)
+
     def dense(c):
-        return np.searchsorted(values, c).astype(np.int32)
+        return lut[c] if lut is not None else np.searchsorted(values, c).astype(np.int32)
 
     c64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     return Packed(
