@@ -489,8 +489,15 @@ ap_kernel(const ApParams p, const Grid101 grid) {
                 int s = s1, i = -1;
                 uint32_t base = n_ens, slot0 = 0;
                 const uint64_t *e = ev;
+                bool tail = false;
                 for (;;) {
-                    if (!FULL && !ow.valid && !os.valid && vw.E == vs.E && vw.k == vs.k && vw.g == vs.g) break;
+                    if (!FULL && !ow.valid && !os.valid) {
+                        // every own detection lies behind: no true positive left in front of either variant -> nothing
+                        // can change any more; both alive with the same count and grid pointer -> continue in the tail loop
+                        const uint32_t kw = vw.dead ? 0u : vw.k, ks = vs.dead ? 0u : vs.k;
+                        if (kw == 0u && ks == 0u) break;
+                        if (!vw.dead && !vs.dead && kw == ks && vw.g == vs.g) { tail = true; break; }
+                    }
                     if (i < 0) {
                         if (s < s1) {                       // leaving a segment: its remaining own detections
                             ow.drain(vw, cw, ge, base, slot0, 0u, t);
@@ -514,6 +521,35 @@ ap_kernel(const ApParams p, const Grid101 grid) {
                         vs.step(cw, ge, pos + os.before());
                     }
                     --i;
+                }
+                // Tail: the variants now see the same ranks and share k, q, r, g (kept in vw); only the envelope values
+                // and the integrals differ, and they stop differing when the envelopes meet.  One ratio per event
+                // serves both variants and events that are not true positives at this threshold cost a load and a test.
+                while (tail && vw.E != vs.E) {
+                    if (i < 0) {
+                        if (s == s0) break;
+                        --s;
+                        base -= tot[(int64_t)s * p.ntp];
+                        e = ev + p.seg_ev0[s];
+                        i = (int)evcnt[(int64_t)s * p.ntp] - 1;
+                        continue;
+                    }
+                    const uint64_t rec = e[i--];
+                    if (!((rec >> (32 + t)) & 1ull)) continue;
+                    const double ratio = fast_ratio(vw.k, base + (uint32_t)rec);
+                    vw.E = fmax(vw.E, ratio);
+                    vs.E = fmax(vs.E, ratio);
+                    --vw.k;
+                    vw.q -= vw.dq;
+                    vw.r -= vw.dr;
+                    if (vw.r < 0) { vw.r += (int)vw.n_l; --vw.q; }
+                    const int gl = vw.first_grid(ge);
+                    if (gl <= vw.g) {
+                        const double d = __dsub_rn(cw[vw.g + 1], cw[gl]);
+                        vw.ap = __dadd_rn(vw.ap, __dmul_rn(vw.E, d));
+                        vs.ap = __dadd_rn(vs.ap, __dmul_rn(vs.E, d));
+                        vw.g = gl - 1;
+                    }
                 }
             }
             ap_w = vw.dead ? 0.0 : vw.ap;
