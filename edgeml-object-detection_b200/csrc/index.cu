@@ -520,7 +520,8 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     // and the AP sweep on COCO-shaped data, profiles/), enough (batch, segment) warp items for >= 4 waves of
     // 148 SMs x 8 warps, and no segment so long that a single warp becomes the tail of the walk.
     const int64_t seg_target = std::max<int64_t>(2 * C, ceil_div(4 * 148 * 8, ix->nbatch));
-    int seg_chunks = seg_chunks_req > 0 ? seg_chunks_req
+    // (an event record keeps its rank inside the segment in 16 bits: at most 2047 chunks = 65504 slots per segment)
+    int seg_chunks = seg_chunks_req > 0 ? std::min(seg_chunks_req, 2047)
                                         : (int)std::min<int64_t>(512, std::max<int64_t>(16, ceil_div(raw_chunks, seg_target)));
     ix->seg_chunks = seg_chunks;
     LD = make_layout(h_hist, C, 1, seg_chunks);

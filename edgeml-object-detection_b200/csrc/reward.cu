@@ -183,7 +183,7 @@ struct WalkParams {
     const uint32_t *bqoff_w, *bqoff_s;   // [nbatch][S+1]
     int64_t Ev;
     uint32_t *evcnt;            // [S][ntp]
-    uint64_t *ev;               // [ntp][Ev]
+    uint32_t *ev;               // [ntp][Ev] event records: rank inside the segment (16 bits) | TP mask << 16
     uint32_t *cb_w, *cb_s;
 };
 
@@ -235,7 +235,7 @@ walk_kernel(const WalkParams p) {
         uint32_t cnt = 0, ecur = 0;
         uint32_t qw = 0, qw_end = 0, qs = 0, qs_end = 0;
         uint2 nqw = make_uint2(0xffffffffu, 0u), nqs = make_uint2(0xffffffffu, 0u);
-        uint64_t *evout = nullptr;
+        uint32_t *evout = nullptr;
         if (DETS) {
             evout = p.ev + tl * p.Ev + p.seg_ev0[s];
             const uint32_t *ow = p.bqoff_w + gb * (p.S + 1) + s;
@@ -265,7 +265,7 @@ walk_kernel(const WalkParams p) {
                     const uint32_t mask = __shfl_sync(kFull, tp, b);
                     if ((word >> b) & 1u) {
                         const uint32_t rank = cnt + __popc(word & ((2u << b) - 1u));   // 1-based, inclusive
-                        evout[ecur++] = (uint64_t)rank | ((uint64_t)mask << 32);
+                        evout[ecur++] = rank | (mask << 16);        // rank <= 65504 slots per segment (index.cu)
                     }
                 }
                 const uint32_t chunk_end = (uint32_t)(ch0 + c + 1) * 32u;
@@ -306,7 +306,7 @@ struct ApParams {
     const int32_t *cls_seg0, *seg_chunk0, *lcls_seg0, *cls_order;
     const uint32_t *seg_ev0;
     const uint32_t *tot, *evcnt, *totL;
-    const uint64_t *ev;
+    const uint32_t *ev;
     const uint32_t *gtcnt;
     const int64_t *w_off, *s_off;
     const uint16_t *own_w_cs, *own_s_cs, *own_w_m, *own_s_m;
@@ -355,9 +355,15 @@ struct ApVar {
         ap = 0.0; E = 0.0; g = 99; k = K; n_l = nl; q = 0; r = 0;
         dead = (K == 0 || n_p == 0);
         if (dead) return;
-        const uint64_t a = (uint64_t)K * 100ull;
-        q = (int)(a / nl);
-        r = (int)(a - (uint64_t)q * nl);
+        if (K <= 42000000u) {               // 100 K fits 32 bits: skip the 64-bit division routine
+            const uint32_t a = K * 100u;
+            q = (int)(a / nl);
+            r = (int)(a - (uint32_t)q * nl);
+        } else {
+            const uint64_t a = (uint64_t)K * 100ull;
+            q = (int)(a / nl);
+            r = (int)(a - (uint64_t)q * nl);
+        }
         dq = (int)(100u / nl);
         dr = (int)(100u - (uint32_t)dq * nl);
         const int gl = first_grid(ge);
@@ -451,19 +457,19 @@ ap_kernel(const ApParams p, const Grid101 grid) {
         if (n_l > 0) {
             if (t == 0) has_gt = 1.0;
             const int s0 = p.cls_seg0[c], s1 = p.cls_seg0[c + 1];
-            const uint64_t *ev = p.ev + tl * p.Ev;
+            const uint32_t *ev = p.ev + tl * p.Ev;
             const uint32_t *tot = p.tot + tl, *evcnt = p.evcnt + tl;
             uint32_t n_ens = 0, K_ens = 0;
             for (int s = s0; s < s1; ++s) {
                 n_ens += tot[(int64_t)s * p.ntp];
-                const uint32_t *eh = reinterpret_cast<const uint32_t *>(ev + p.seg_ev0[s]) + 1;   // mask halves of the records
+                const uint32_t *e = ev + p.seg_ev0[s];
                 const int ne = (int)evcnt[(int64_t)s * p.ntp];
                 int i = 0;
                 for (; i + 4 <= ne; i += 4) {           // four independent loads in flight
-                    const uint32_t a = eh[2 * i], b = eh[2 * i + 2], c2 = eh[2 * i + 4], d = eh[2 * i + 6];
-                    K_ens += ((a >> t) & 1u) + ((b >> t) & 1u) + ((c2 >> t) & 1u) + ((d >> t) & 1u);
+                    const uint32_t a = e[i], b = e[i + 1], c2 = e[i + 2], d = e[i + 3];
+                    K_ens += ((a >> (16 + t)) & 1u) + ((b >> (16 + t)) & 1u) + ((c2 >> (16 + t)) & 1u) + ((d >> (16 + t)) & 1u);
                 }
-                for (; i < ne; ++i) K_ens += (eh[2 * i] >> t) & 1u;
+                for (; i < ne; ++i) K_ens += (e[i] >> (16 + t)) & 1u;
             }
             const uint16_t *wcs = p.own_w_cs + j * (p.C + 1) + c, *scs = p.own_s_cs + j * (p.C + 1) + c;
             const int wa = wcs[0], wb = wcs[1], sa = scs[0], sb = scs[1];
@@ -488,7 +494,7 @@ ap_kernel(const ApParams p, const Grid101 grid) {
                 // with different segment structure do not wait for each other at segment boundaries
                 int s = s1, i = -1;
                 uint32_t base = n_ens, slot0 = 0;
-                const uint64_t *e = ev;
+                const uint32_t *e = ev;
                 bool tail = false;
                 for (;;) {
                     if (!FULL && !ow.valid && !os.valid) {
@@ -511,12 +517,12 @@ ap_kernel(const ApParams p, const Grid101 grid) {
                         i = (int)evcnt[(int64_t)s * p.ntp] - 1;
                         continue;
                     }
-                    const uint64_t rec = e[i];
-                    const uint32_t pos = base + (uint32_t)rec;
+                    const uint32_t rec = e[i];
+                    const uint32_t pos = base + (rec & 0xffffu);
                     // own detections that rank behind this event come first in the reverse sweep
                     ow.drain(vw, cw, ge, base, slot0, pos, t);
                     os.drain(vs, cw, ge, base, slot0, pos, t);
-                    if ((rec >> (32 + t)) & 1ull) {
+                    if ((rec >> (16 + t)) & 1u) {
                         vw.step(cw, ge, pos + ow.before());
                         vs.step(cw, ge, pos + os.before());
                     }
@@ -534,9 +540,9 @@ ap_kernel(const ApParams p, const Grid101 grid) {
                         i = (int)evcnt[(int64_t)s * p.ntp] - 1;
                         continue;
                     }
-                    const uint64_t rec = e[i--];
-                    if (!((rec >> (32 + t)) & 1ull)) continue;
-                    const double ratio = fast_ratio(vw.k, base + (uint32_t)rec);
+                    const uint32_t rec = e[i--];
+                    if (!((rec >> (16 + t)) & 1u)) continue;
+                    const double ratio = fast_ratio(vw.k, base + (rec & 0xffffu));
                     vw.E = fmax(vw.E, ratio);
                     vs.E = fmax(vs.E, ratio);
                     --vw.k;
@@ -606,7 +612,7 @@ static WsLayout ws_layout(const orie_index *ix, int64_t nt) {
     L.tot = take(ix->S * ntp * 4);
     L.evcnt = take(ix->S * ntp * 4);
     L.totL = take(ix->SL * ntp * 4);
-    L.ev = take(ntp * ix->Ev * 8);
+    L.ev = take(ntp * ix->Ev * 4);
     L.cb_w = take(ix->Dw * 4);
     L.cb_s = take(ix->Ds * 4);
     L.partial = take(ntp * ix->class_groups * 3 * 8);
@@ -760,7 +766,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         wp.bq_w = ix->bq_w; wp.bq_s = ix->bq_s; wp.bqoff_w = ix->bqoff_w; wp.bqoff_s = ix->bqoff_s;
         wp.Ev = ix->Ev;
         wp.evcnt = (uint32_t *)(ws + L.evcnt);
-        wp.ev = (uint64_t *)(ws + L.ev);
+        wp.ev = (uint32_t *)(ws + L.ev);
         wp.cb_w = (uint32_t *)(ws + L.cb_w);
         wp.cb_s = (uint32_t *)(ws + L.cb_s);
         dim3 grid((unsigned)nb, (unsigned)ceil_div(ix->S, wp.segs_per_block));
@@ -776,7 +782,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     ap.S = ix->S; ap.SL = ix->SL; ap.Ev = ix->Ev;
     ap.cls_order = ix->cls_order; ap.cls_seg0 = ix->cls_seg0; ap.seg_chunk0 = ix->seg_chunk0; ap.lcls_seg0 = ix->lcls_seg0; ap.seg_ev0 = ix->seg_ev0;
     ap.tot = (const uint32_t *)(ws + L.tot); ap.evcnt = (const uint32_t *)(ws + L.evcnt);
-    ap.totL = (const uint32_t *)(ws + L.totL); ap.ev = (const uint64_t *)(ws + L.ev);
+    ap.totL = (const uint32_t *)(ws + L.totL); ap.ev = (const uint32_t *)(ws + L.ev);
     ap.gtcnt = ix->gtcnt; ap.w_off = ix->w_off; ap.s_off = ix->s_off;
     ap.own_w_cs = ix->own_w_cs; ap.own_s_cs = ix->own_s_cs; ap.own_w_m = ix->own_w_m; ap.own_s_m = ix->own_s_m;
     ap.own_w_q = ix->own_w_q; ap.own_s_q = ix->own_s_q;
