@@ -152,3 +152,57 @@ def test_class_sharded_sums_add_up():
     a = Engine(class_shard(pk, 0, world), iouv=O.IOU_05).sample_bits(N, seed=3)
     b = Engine(class_shard(pk, 2, world), iouv=O.IOU_05).sample_bits(N, seed=3)
     assert np.array_equal(a, b)
+
+
+def test_multi_tile_sort_path_matches(monkeypatch):
+    """The cooperative radix sort keeps a CTA's items in registers when they fit one tile; larger ranges (the 50k
+    sweep) stream tile by tile.  Force that path on a small dataset (2 CTAs for ~35 k detections) and demand
+    identical bits, TP flags included."""
+    M, N = 300, 120
+    _, pk = make_packed(M=M, seed=61)
+    em = O.ensemble_matrix(M, N, 4)
+    eng = _engine(pk, O.IOU_05_095)
+    ref, ref_detail = eng.orie(N, ens_matrix=em, detail=True)
+    ref_dev = eng.orie(N, seed=17)
+    monkeypatch.setenv("ORIE_SORT_MAX_BLOCKS", "2")
+    eng2 = _engine(pk, O.IOU_05_095)
+    got, got_detail = eng2.orie(N, ens_matrix=em, detail=True)
+    got_dev = eng2.orie(N, seed=17)
+    monkeypatch.delenv("ORIE_SORT_MAX_BLOCKS")
+    assert eng.info == eng2.info
+    assert np.array_equal(ref, got) and np.array_equal(ref_detail, got_detail) and np.array_equal(ref_dev, got_dev)
+    eng.close(); eng2.close()
+
+
+def _orie_with_the_engine_tie_rule(i, wd, sd, lc, ens):
+    """The oracle evaluated in the engine's documented tie order: equal confidences sort weak before strong, then by
+    image index, then by row — i.e. a stable sort of the records concatenated in image order, the target's strong
+    record last."""
+    ens = np.sort(np.asarray(ens, dtype=np.int64))
+    gt = np.concatenate([lc[s] for s in list(ens) + [i]]).astype(int)
+    cat = lambda recs: [np.concatenate(col, axis=0) for col in zip(*recs)]
+    weak_ap = O.ap_by_class(*cat([wd[s] for s in np.sort(np.append(ens, i))]), gt)
+    strong_ap = O.ap_by_class(*cat([wd[s] for s in ens] + [sd[i]]), gt)
+    r = (np.mean(strong_ap) - np.mean(weak_ap)) * (len(ens) + 1) if len(gt) else 0.0
+    return 0.0 if np.isnan(r) else float(r)
+
+
+def test_confidence_ties_and_many_classes_follow_the_tie_rule():
+    """Exact confidence ties (as in %g-rounded files) are machine-dependent upstream (unstable argsort); the engine
+    sorts them weak before strong, then by image, then by row (tie rule).  300 class ids exercise the
+    two-pass class digit of the sort."""
+    M, N = 90, 30
+    ds, pk = make_packed(M=M, seed=8)
+    pk.w_conf[:] = np.round(pk.w_conf, 2)                    # heavy ties inside and across images and detectors
+    pk.s_conf[:] = np.round(pk.s_conf, 2)
+    remap = np.random.default_rng(0).permutation(300)[:pk.num_classes].astype(np.int32)   # spread over [0, 300)
+    pk.w_cls[:] = remap[pk.w_cls]; pk.s_cls[:] = remap[pk.s_cls]; pk.l_cls[:] = remap[pk.l_cls]
+    pk.num_classes = 300
+    pk.class_values = np.arange(300, dtype=np.int64)
+    eng = _engine(pk, O.IOU_05_095)
+    em = O.ensemble_matrix(M, N, 13)
+    got = eng.orie(N, ens_matrix=em)
+    wd, sd, lc = oracle_cache(pk, O.IOU_05_095)
+    want = np.array([_orie_with_the_engine_tie_rule(i, wd, sd, lc, em[i]) for i in range(M)])
+    assert np.abs(got - want).max() < 1e-9
+    eng.close()
