@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=32, help="targets in the single-thread CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seg-chunks", type=int, default=0, help="segment length override (0 = engine default)")
-    ap.add_argument("--shard", default="classes", choices=["classes", "targets"],
+    ap.add_argument("--shard", default="auto", choices=["auto", "classes", "targets"],
                     help="multi-GPU decomposition: classes (whole pipeline shrinks per rank, one all-reduce of 3 doubles "
                          "per target) or targets (index replicated, one all-gather of reward slices)")
     ap.add_argument("--workspace-gb", type=int, default=16, help="reward-pass workspace budget; targets run in waves that fit")
@@ -212,7 +212,7 @@ def run_b200(args):
     import torch.distributed as dist
     import orie_b200  # noqa: F401
     from orie_b200 import _lib
-    from orie_b200.engine import DevicePacked, Engine, HostPacked, class_shard, rewards_from_sums, shard_range
+    from orie_b200.engine import DevicePacked, Engine, HostPacked, class_shard, pick_shard, rewards_from_sums, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -228,7 +228,7 @@ def run_b200(args):
 
     ds, pk, N, iouv = dataset(args.workload, args.num_images)
     M, T = pk.num_images, len(iouv)
-    by_class = world > 1 and args.shard == "classes"
+    by_class = world > 1 and pick_shard(pk.num_images, args.shard) == "classes"
     pk_all = pk
     if by_class:
         pk = class_shard(pk_all, rank, world)        # this rank's classes, all images (host-side partition, untimed)

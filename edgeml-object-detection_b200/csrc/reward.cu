@@ -212,7 +212,10 @@ walk_kernel(const WalkParams p) {
     extern __shared__ uint32_t memb_s[];   // [ens_words * 32]: bit j of memb[img] = img in ensemble of target 32*batch+j
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kWarps = blockDim.x >> 5;
-    const int64_t lb = blockIdx.x;                 // local batch
+    // GMEM: blocks of one batch are neighbours in launch order (x = segment group), so the tables of the
+    // batches in flight at any time stay L2-resident (a few dozen x 200 KB instead of one per resident block)
+    const int64_t lb = GMEM ? blockIdx.y : blockIdx.x;   // local batch
+    const int64_t yb = GMEM ? blockIdx.x : blockIdx.y;   // segment group
     const int64_t tl = lb * 32 + lane;             // local target of this lane
     Transposer transpose;
     transpose.init(lane);
@@ -227,7 +230,7 @@ walk_kernel(const WalkParams p) {
         __syncthreads();
     }
     const int64_t gb = (p.t0 >> 5) + lb;           // global batch (query lists are per global batch)
-    const int64_t sbeg = (int64_t)blockIdx.y * p.segs_per_block;
+    const int64_t sbeg = yb * p.segs_per_block;
     const int64_t send = min(sbeg + p.segs_per_block, p.S);
     for (int64_t s = sbeg + warp; s < send; s += kWarps) {
         const int64_t ch0 = p.seg_chunk0[s];
@@ -734,11 +737,17 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         const char *tune = getenv("ORIE_WALK_WAVES");          // developer knob (profiles/tune.py)
         const double waves = tune ? atof(tune) : 2.0;
         int64_t want_y = (int64_t)((waves * (double)resident + (double)nb - 1.0) / (double)nb);
+        if (gmem) want_y = std::max<int64_t>(want_y, 32);     // many blocks per batch: few tables in flight
         int64_t spb = ceil_div(S, want_y > 0 ? want_y : 1);
         const int64_t warps = walk_threads / 32;
         spb = round_up(spb > 0 ? spb : 1, warps);
         return (int)spb;
     };
+    if (gmem && nb > 65535) {
+        set_error("orie_reward: at most %d targets per call for datasets of this size (%lld requested); run them in waves",
+                  65535 * 32, (long long)nt);
+        return ORIE_ELIMIT;
+    }
     if (marks) ORIE_CUDA(cudaEventRecord(marks[0], stream));
     if (gmem) {
         wp.memb_global = (uint32_t *)(ws + L.memb);
@@ -752,7 +761,8 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         lp.slot_img = ix->lab_slot_img; lp.seg_chunk0 = ix->lseg_chunk0; lp.seg_nch = ix->lseg_nch;
         lp.S = ix->SL; lp.segs_per_block = segs_per_block(ix->SL);
         lp.tot = (uint32_t *)(ws + L.totL);
-        dim3 grid((unsigned)nb, (unsigned)ceil_div(ix->SL, lp.segs_per_block));
+        const unsigned ny = (unsigned)ceil_div(ix->SL, lp.segs_per_block);
+        dim3 grid = gmem ? dim3(ny, (unsigned)nb) : dim3((unsigned)nb, ny);
         ORIE_TRY(launch_walk<false>(grid, walk_threads, smem, gmem, stream, lp));
         ORIE_LAUNCH_CHECK();
     }
@@ -769,7 +779,8 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         wp.ev = (uint32_t *)(ws + L.ev);
         wp.cb_w = (uint32_t *)(ws + L.cb_w);
         wp.cb_s = (uint32_t *)(ws + L.cb_s);
-        dim3 grid((unsigned)nb, (unsigned)ceil_div(ix->S, wp.segs_per_block));
+        const unsigned ny = (unsigned)ceil_div(ix->S, wp.segs_per_block);
+        dim3 grid = gmem ? dim3(ny, (unsigned)nb) : dim3((unsigned)nb, ny);
         ORIE_TRY(launch_walk<true>(grid, walk_threads, smem, gmem, stream, wp));
         ORIE_LAUNCH_CHECK();
     }

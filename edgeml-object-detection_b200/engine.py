@@ -84,6 +84,16 @@ def class_shard(packed: Packed, rank: int, world: int) -> Packed:
                   l_off=l_off, l_box=l_box, l_cls=l_cls)
 
 
+def pick_shard(num_images: int, shard: str = "auto") -> str:
+    """Multi-GPU decomposition.  ``classes`` shrinks every phase (matching, index, walk, AP) with the rank count and
+    is the better choice while the 32-target membership table of the walk fits shared memory (about 28 k images);
+    beyond that the walk is bound by table lookups that do not shrink with the class count, and ``targets`` wins
+    (measured on the 50 k-image sweep, profiles/)."""
+    if shard != "auto":
+        return shard
+    return "classes" if ((num_images + 1 + 31) // 32) * 32 * 4 <= 112 * 1024 else "targets"
+
+
 def rewards_from_sums(sums, T: int, n_used: int):
     """(mean strong AP - mean weak AP) * (N + 1) from per-target sums (torch or numpy), NaN -> 0 (reward.py:50,86)."""
     sw, ss, nc = sums[:, 0], sums[:, 1], sums[:, 2]
@@ -409,15 +419,15 @@ class Engine:
 
 
 def compute_rewards(packed: Packed, method: str = "orie", num_ensemble: int = 1000, iouv=IOU_05, ens_matrix=None,
-                    seed: int = 0, device=None, distributed: bool = False, shard: str = "classes"):
+                    seed: int = 0, device=None, distributed: bool = False, shard: str = "auto"):
     """Reward vector of the whole dataset (what ``reward.py:main`` computes between its two timers, plus
     ``set_data``'s matching).  With ``distributed=True`` (under torchrun, NCCL) the work is split over the ranks:
 
-    * ``shard="classes"`` (default): every rank keeps all images but only the detections / labels of its share of
+    * ``shard="classes"`` (what ``"auto"`` picks up to ~28 k images): every rank keeps all images but only the detections / labels of its share of
       the classes, runs the whole pipeline on that shard for ALL targets, and the per-target AP sums (3 doubles per
       target) are combined with one all-reduce.  Matching, the index build, the walk and the AP sweep all shrink
       with the rank count.
-    * ``shard="targets"``: every rank holds the whole dataset and computes a contiguous block of targets; the
+    * ``shard="targets"`` (``"auto"`` beyond that): every rank holds the whole dataset and computes a contiguous block of targets; the
       reward slices are combined with one all-gather (the index build is replicated)."""
     method = method.lower()
     if method == "ori":
@@ -433,6 +443,7 @@ def compute_rewards(packed: Packed, method: str = "orie", num_ensemble: int = 10
             eng.close()
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
+    shard = pick_shard(M, shard)
     if shard == "classes":
         eng = Engine(class_shard(packed, rank, world), iouv=iouv, device=device)
         try:
