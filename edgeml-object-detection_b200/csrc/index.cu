@@ -208,44 +208,36 @@ __global__ void own_class_start_kernel(const uint16_t *__restrict__ own_w_c, con
     }
 }
 
-// Batch-major order (the (class, conf) order stably regrouped by 32-image batch): the weak rows of a batch, ascending
-// by query slot, are the entries [w_off[32b], w_off[32b + 32]) of bq_w — again addressed by the weak rank.
-__global__ void batch_query_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ wrank,
-                                   const uint32_t *__restrict__ img_all, int64_t n, const uint32_t *__restrict__ q_of_det,
-                                   const uint32_t *__restrict__ ownpos, uint2 *__restrict__ bq_w, uint2 *__restrict__ bq_s) {
+// Batch-major order (the (class, conf) order stably regrouped by 32-image batch): position v IS the entry of the
+// batch's query list, which is therefore ascending by query slot with weak and strong rows interleaved.
+__global__ void batch_query_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ img_all,
+                                   int64_t n, const uint32_t *__restrict__ q_of_det, const uint32_t *__restrict__ ownpos,
+                                   uint2 *__restrict__ bq) {
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const uint32_t u = order[v];
-    const uint2 e = make_uint2(q_of_det[u], ((img_all[u] & 31u) << 27) | ownpos[u]);
-    if (u < d.Dw) bq_w[wrank[v]] = e;
-    else bq_s[(uint32_t)v - wrank[v]] = e;
+    bq[v] = make_uint2(q_of_det[u] | (u >= d.Dw ? 0x80000000u : 0u), ((img_all[u] & 31u) << 27) | ownpos[u]);
 }
 
-// bqoff[b][s] = first entry of batch b with q >= first slot of segment s  (s == S: end of the batch); both detectors
-__global__ void batch_query_offsets_kernel(const uint2 *__restrict__ bq_w, const int64_t *__restrict__ w_off,
-                                           uint32_t *__restrict__ bqoff_w, const uint2 *__restrict__ bq_s,
-                                           const int64_t *__restrict__ s_off, uint32_t *__restrict__ bqoff_s, int64_t M,
+// bqoff[b][s] = first entry of batch b with q >= first slot of segment s  (s == S: end of the batch)
+__global__ void batch_query_offsets_kernel(const uint2 *__restrict__ bq, const int64_t *__restrict__ w_off,
+                                           const int64_t *__restrict__ s_off, uint32_t *__restrict__ bqoff, int64_t M,
                                            int64_t nbatch, const int32_t *__restrict__ seg_chunk0, int64_t S) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t per = nbatch * (S + 1);
-    if (k >= 2 * per) return;
-    const bool strong = k >= per;
-    if (strong) k -= per;
-    const uint2 *bq = strong ? bq_s : bq_w;
-    const int64_t *off = strong ? s_off : w_off;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nbatch * (S + 1)) return;
     const int64_t b = k / (S + 1), s = k % (S + 1);
     const int64_t i0 = b * 32 < M ? b * 32 : M, i1 = (b + 1) * 32 < M ? (b + 1) * 32 : M;
-    int64_t lo = off[i0], hi = off[i1];
+    int64_t lo = w_off[i0] + s_off[i0], hi = w_off[i1] + s_off[i1];
     if (s < S) {
         const uint32_t slot0 = (uint32_t)seg_chunk0[s] * 32u;
         while (lo < hi) {
             int64_t mid = (lo + hi) >> 1;
-            if (bq[mid].x < slot0) lo = mid + 1; else hi = mid;
+            if ((bq[mid].x & 0x7fffffffu) < slot0) lo = mid + 1; else hi = mid;
         }
     } else {
         lo = hi;
     }
-    (strong ? bqoff_s : bqoff_w)[k] = (uint32_t)lo;
+    bqoff[k] = (uint32_t)lo;
 }
 
 // r-th label in class order -> its slot of the padded label stream
@@ -412,13 +404,12 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&ix->own_s_m, Ds);
     A.add(&ix->own_w_cs, M * (C + 1));
     A.add(&ix->own_s_cs, M * (C + 1));
-    A.add(&ix->bq_w, Dw);
-    A.add(&ix->bq_s, Ds);
+    A.add(&ix->bq, n);
     A.add(&ix->gtcnt, M * C);
     ORIE_TRY(B.keep(A));
 
     uint64_t *keys, *keys_tmp;
-    uint32_t *vtmp, *img_all, *img_l, *order, *ord_img, *ord_bat, *rank_img, *rank_bat, *lorder, *meta, *wpre, *q_of_det, *ownpos, *d_total;
+    uint32_t *vtmp, *img_all, *img_l, *order, *ord_img, *ord_bat, *rank_img, *lorder, *meta, *wpre, *q_of_det, *ownpos, *d_total;
     uint16_t *own_w_c, *own_s_c;
     char *scratch;
     A.add(&keys, n);
@@ -430,7 +421,6 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&ord_img, n);
     A.add(&ord_bat, n);
     A.add(&rank_img, n);
-    A.add(&rank_bat, n);
     A.add(&lorder, G);
     A.add(&meta, 3 * C + 1);
     A.add(&wpre, n);
@@ -472,8 +462,8 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         ORIE_TRY(sort_add_passes(&j, kDigitKey, 0, 64));
         ORIE_TRY(sort_add_passes(&j, kDigitClass, 0, cbits));
         ORIE_TRY(sort_run(j, sort_blocks, scratch, st));
-        // the same order regrouped by image and by 32-image batch (both detectors at once); the rank epilogue
-        // separates weak from strong rows, which saves the detector bit of the key (one pass at COCO scale)
+        // the same order regrouped by image (the rank epilogue separates weak from strong rows, which saves the
+        // detector bit of the key) and by 32-image batch (weak and strong rows stay interleaved)
         SortJob r;
         r.n = n;
         r.vals_in = order; r.vals_a = ord_img; r.vals_b = vtmp;
@@ -483,7 +473,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         ORIE_TRY(sort_run(r, sort_blocks, scratch, st));
         r.npass = 0;
         r.vals_a = ord_bat;
-        r.rank_out = rank_bat;
+        r.rank_out = nullptr;
         ORIE_TRY(sort_add_passes(&r, kDigitBatch, 0, bbits));
         ORIE_TRY(sort_run(r, sort_blocks, scratch, st));
     }
@@ -553,8 +543,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&ix->slot_tp, ix->P);
     A.add(&ix->evbase, ix->nchunks);
     A.add(&ix->seg_ev0, ix->S);
-    A.add(&ix->bqoff_w, ix->nbatch * (ix->S + 1));
-    A.add(&ix->bqoff_s, ix->nbatch * (ix->S + 1));
+    A.add(&ix->bqoff, ix->nbatch * (ix->S + 1));
     A.add(&ix->lab_slot_img, ix->PL);
     ORIE_TRY(B.keep(A));
     tab.bind(d_tables);
@@ -591,14 +580,14 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         own_fill_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_img, rank_img, n, q_of_det, ix->own_w_q, ix->own_w_m, own_w_c,
                                                    ix->own_s_q, ix->own_s_m, own_s_c, ownpos);
         ORIE_LAUNCH_CHECK();
-        batch_query_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_bat, rank_bat, img_all, n, q_of_det, ownpos, ix->bq_w, ix->bq_s);
+        batch_query_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_bat, img_all, n, q_of_det, ownpos, ix->bq);
         ORIE_LAUNCH_CHECK();
     }
     own_class_start_kernel<<<grid_for(2 * M * 32), 256, 0, st>>>(own_w_c, ix->w_off, ix->own_w_cs, own_s_c, ix->s_off,
                                                                ix->own_s_cs, M, C);
     ORIE_LAUNCH_CHECK();
-    batch_query_offsets_kernel<<<grid_for(2 * ix->nbatch * (ix->S + 1)), 256, 0, st>>>(
-        ix->bq_w, ix->w_off, ix->bqoff_w, ix->bq_s, ix->s_off, ix->bqoff_s, M, ix->nbatch, ix->seg_chunk0, ix->S);
+    batch_query_offsets_kernel<<<grid_for(ix->nbatch * (ix->S + 1)), 256, 0, st>>>(ix->bq, ix->w_off, ix->s_off, ix->bqoff, M,
+                                                                                 ix->nbatch, ix->seg_chunk0, ix->S);
     ORIE_LAUNCH_CHECK();
 
     // ---- label stream

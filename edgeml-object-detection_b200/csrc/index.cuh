@@ -22,11 +22,9 @@ struct orie_index {
     int32_t *cls_seg0 = nullptr;     // [C+1]
     int32_t *cls_order = nullptr;    // [C] classes by descending weak-detection count (AP warps take neighbours)
 
-    // ---- per-batch query lists: the own detections of a batch's 32 images, ascending by query slot
-    uint2 *bq_w = nullptr;           // [Dw] {q, lane << 27 | own position}
-    uint2 *bq_s = nullptr;           // [Ds]
-    uint32_t *bqoff_w = nullptr;     // [nbatch][S+1] first entry of (batch, segment)
-    uint32_t *bqoff_s = nullptr;
+    // ---- per-batch query list: the own detections (both detectors) of a batch's 32 images, ascending by query slot
+    uint2 *bq = nullptr;             // [Dw + Ds] {q | is_strong << 31, lane << 27 | own position}
+    uint32_t *bqoff = nullptr;       // [nbatch][S+1] first entry of (batch, segment)
 
     // ---- own lists: image-major (aligned with w_off / s_off), (class asc, conf desc)
     int64_t *w_off = nullptr, *s_off = nullptr;   // [M+1] device copies

@@ -179,8 +179,8 @@ struct WalkParams {
     // detection stream only
     const uint16_t *slot_tp;
     const uint32_t *seg_ev0;
-    const uint2 *bq_w, *bq_s;
-    const uint32_t *bqoff_w, *bqoff_s;   // [nbatch][S+1]
+    const uint2 *bq;            // per-batch query list (both detectors), ascending by slot
+    const uint32_t *bqoff;      // [nbatch][S+1]
     int64_t Ev;
     uint32_t *evcnt;            // [S][ntp]
     uint32_t *ev;               // [ntp][Ev] event records: rank inside the segment (16 bits) | TP mask << 16
@@ -204,10 +204,12 @@ __global__ void membership_table_kernel(const WalkParams p) {
 }
 
 // THREADS is the block size the kernel is launched with (256 / 512 / 1024, chosen from the size of the
-// membership table); the register cap keeps 1536+ threads resident per SM.  GMEM: the membership table was
+// membership table); the register cap keeps kWalkResident threads resident per SM (at 1536 the compiler
+// re-materialised the transposer's per-lane constants inside the chunk loop: 13 % more instructions).  GMEM: the membership table was
 // built by membership_table_kernel and is read through L1 instead of shared memory.
+constexpr int kWalkResident = 1280;
 template <bool DETS, int THREADS, bool GMEM>
-__global__ void __launch_bounds__(THREADS, 1536 / THREADS > 0 ? 1536 / THREADS : 1)
+__global__ void __launch_bounds__(THREADS, kWalkResident / THREADS > 0 ? kWalkResident / THREADS : 1)
 walk_kernel(const WalkParams p) {
     extern __shared__ uint32_t memb_s[];   // [ens_words * 32]: bit j of memb[img] = img in ensemble of target 32*batch+j
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -236,17 +238,14 @@ walk_kernel(const WalkParams p) {
         const int64_t ch0 = p.seg_chunk0[s];
         const int nch = p.seg_nch[s];
         uint32_t cnt = 0, ecur = 0;
-        uint32_t qw = 0, qw_end = 0, qs = 0, qs_end = 0;
-        uint2 nqw = make_uint2(0xffffffffu, 0u), nqs = make_uint2(0xffffffffu, 0u);
+        uint32_t qi = 0, q_end = 0;
+        uint2 nq = make_uint2(0xffffffffu, 0u);
         uint32_t *evout = nullptr;
         if (DETS) {
             evout = p.ev + tl * p.Ev + p.seg_ev0[s];
-            const uint32_t *ow = p.bqoff_w + gb * (p.S + 1) + s;
-            const uint32_t *os = p.bqoff_s + gb * (p.S + 1) + s;
-            qw = ow[0]; qw_end = ow[1];
-            qs = os[0]; qs_end = os[1];
-            if (qw < qw_end) nqw = p.bq_w[qw];
-            if (qs < qs_end) nqs = p.bq_s[qs];
+            const uint32_t *o = p.bqoff + gb * (p.S + 1) + s;
+            qi = o[0]; q_end = o[1];
+            if (qi < q_end) nq = p.bq[qi];
         }
         const uint32_t *simg = p.slot_img + ch0 * 32 + lane;
         const uint16_t *stp = DETS ? p.slot_tp + ch0 * 32 + lane : nullptr;
@@ -272,17 +271,11 @@ walk_kernel(const WalkParams p) {
                     }
                 }
                 const uint32_t chunk_end = (uint32_t)(ch0 + c + 1) * 32u;
-                while (nqw.x < chunk_end) {                     // uniform: own weak detections in this chunk
-                    if (lane == (int)(nqw.y >> 27))
-                        p.cb_w[nqw.y & 0x07ffffffu] = cnt + __popc(word & ((1u << (nqw.x & 31u)) - 1u));
-                    ++qw;
-                    nqw = qw < qw_end ? p.bq_w[qw] : make_uint2(0xffffffffu, 0u);
-                }
-                while (nqs.x < chunk_end) {                     // uniform: own strong detections inserted here
-                    if (lane == (int)(nqs.y >> 27))
-                        p.cb_s[nqs.y & 0x07ffffffu] = cnt + __popc(word & ((1u << (nqs.x & 31u)) - 1u));
-                    ++qs;
-                    nqs = qs < qs_end ? p.bq_s[qs] : make_uint2(0xffffffffu, 0u);
+                while ((nq.x & 0x7fffffffu) < chunk_end) {       // uniform: own detections (weak: sitting, strong: inserted) in this chunk
+                    if (lane == (int)(nq.y >> 27))
+                        ((nq.x >> 31) ? p.cb_s : p.cb_w)[nq.y & 0x07ffffffu] = cnt + __popc(word & ((1u << (nq.x & 31u)) - 1u));
+                    ++qi;
+                    nq = qi < q_end ? p.bq[qi] : make_uint2(0xffffffffu, 0u);
                 }
             }
             cnt += __popc(word);
@@ -733,7 +726,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     auto segs_per_block = [&](int64_t S) {
         // enough blocks for two full waves of resident blocks (2048 threads per SM) when the data allows,
         // at least one segment per warp
-        const int64_t resident = 148 * (1536 / walk_threads > 0 ? 1536 / walk_threads : 1);
+        const int64_t resident = 148 * (kWalkResident / walk_threads > 0 ? kWalkResident / walk_threads : 1);
         const char *tune = getenv("ORIE_WALK_WAVES");          // developer knob (profiles/tune.py)
         const double waves = tune ? atof(tune) : 2.0;
         int64_t want_y = (int64_t)((waves * (double)resident + (double)nb - 1.0) / (double)nb);
@@ -773,7 +766,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         wp.S = ix->S; wp.segs_per_block = segs_per_block(ix->S);
         wp.tot = (uint32_t *)(ws + L.tot);
         wp.slot_tp = ix->slot_tp; wp.seg_ev0 = ix->seg_ev0;
-        wp.bq_w = ix->bq_w; wp.bq_s = ix->bq_s; wp.bqoff_w = ix->bqoff_w; wp.bqoff_s = ix->bqoff_s;
+        wp.bq = ix->bq; wp.bqoff = ix->bqoff;
         wp.Ev = ix->Ev;
         wp.evcnt = (uint32_t *)(ws + L.evcnt);
         wp.ev = (uint32_t *)(ws + L.ev);
