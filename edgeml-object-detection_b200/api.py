@@ -15,7 +15,7 @@ from pathlib import Path
 import numpy as np
 
 from . import data
-from .engine import IOU_05, IOU_05_095, Engine, class_shard, clamp_ensemble, rewards_from_sums, shard_range
+from .engine import IOU_05, IOU_05_095, Engine, class_shard, clamp_ensemble, pick_shard, rewards_from_sums, shard_range
 
 
 def parse_iou_thresholds(spec) -> np.ndarray:
@@ -87,7 +87,8 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
     index build, the ensemble draw and the reward kernels; loading and TP
     matching are reported separately in ``info`` like upstream's ``set_data``.
     Under torchrun (WORLD_SIZE > 1) the classes are sharded over the ranks and the
-    per-target AP sums are combined with one NCCL all-reduce."""
+    per-target AP sums are combined with one NCCL all-reduce; datasets beyond ~28 k images
+    shard the targets instead (one all-gather of reward slices), see ``engine.pick_shard``."""
     import torch
     method = method.lower()
     if method == "ori":
@@ -126,7 +127,8 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
     # Multi-GPU: every rank keeps all images and its share of the classes (AP sums are additive over classes), runs
     # the whole pipeline for all targets and one all-reduce of 3 doubles per target combines the ranks.
     from .engine import HostPacked
-    by_class = dist is not None and method == "orie"
+    by_class = dist is not None and method == "orie" and pick_shard(M) == "classes"
+    by_target = dist is not None and method == "orie" and not by_class
     eng = Engine(HostPacked(class_shard(pk, rank, world) if by_class else pk), iouv=iouv, device=device)
     torch.cuda.synchronize()
     t_match = time.perf_counter() - t
@@ -141,6 +143,16 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
                 eng.stream.synchronize()
                 dist.all_reduce(sums)
                 reward = rewards_from_sums(sums, eng.T, clamp_ensemble(M, N)).cpu().numpy()
+            elif by_target:
+                t0, nt = shard_range(M, rank, world)
+                per = shard_range(M, 0, world)[1]
+                mine = torch.zeros(per, dtype=torch.float64, device=eng.device)
+                if nt > 0:
+                    mine[:nt] = eng.orie_device(N, ens_matrix=None if em is None else em[t0:t0 + nt], seed=seed, t0=t0, nt=nt)
+                gathered = torch.empty(per * world, dtype=torch.float64, device=eng.device)
+                eng.stream.synchronize()
+                dist.all_gather_into_tensor(gathered, mine)
+                reward = gathered[:M].cpu().numpy()
             else:
                 reward = eng.orie_device(N, ens_matrix=em, seed=seed).cpu().numpy()
             eng.check_status()
