@@ -46,13 +46,12 @@ static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b
 // launch.  The digit of a pass is 8 bits (or fewer) of
 //   kDigitKey            the item's 64-bit key                  (key passes must come first)
 //   kDigitClass          the class of the value u, a combined row id: u < split ? cls_lo[u] : cls_hi[u - split]
-//   kDigitImage          img[u]
 //   kDigitBatch          img[u] / 32
 // vals_in == nullptr means the identity (value = position).  The sorted values always end in vals_a
 // (vals_a, vals_b: two buffers of n values, distinct from vals_in); keys0 holds the input keys and is
 // overwritten, keys1 is a second buffer of n keys; the sorted keys are not kept.
 // rank_out (optional): rank_out[v] = number of sorted values < rank_split in front of position v.
-enum { kDigitKey = 0, kDigitClass = 1, kDigitImage = 2, kDigitBatch = 3 };
+enum { kDigitKey = 0, kDigitClass = 1, kDigitBatch = 2 };
 constexpr int kMaxSortPasses = 12;
 struct SortPass {
     int kind, shift;

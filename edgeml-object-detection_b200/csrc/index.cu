@@ -107,13 +107,15 @@ __global__ void init_slots_kernel(uint32_t *__restrict__ slot_img, uint16_t *__r
 __global__ void place_slots_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ wpre,
                                    const uint32_t *__restrict__ img_all, int64_t n, const uint32_t *__restrict__ cls_off,
                                    const uint32_t *__restrict__ pad_off, uint32_t *__restrict__ slot_img,
-                                   uint16_t *__restrict__ slot_tp, uint32_t *__restrict__ q_of_det) {
+                                   uint16_t *__restrict__ slot_tp, uint32_t *__restrict__ q_of_det,
+                                   uint32_t *__restrict__ pos_of_det) {
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const uint32_t u = order[v];
     const int c = d.cls(u);
     const uint32_t slot = pad_off[c] + (wpre[v] - cls_off[c]);
     q_of_det[u] = slot;       // weak: its own slot; strong: the slot it would be inserted in front of
+    pos_of_det[u] = (uint32_t)v;
     if (u < d.Dw) {
         slot_img[slot] = img_all[u];
         slot_tp[slot] = d.w_tp[u];
@@ -163,24 +165,37 @@ events_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks, int64_t per
         seg_ev0[s] = __ldcg(evbase + seg_chunk0[s]);
 }
 
-// Image-major order (the (class, conf) order stably regrouped by image; weak and strong rows of an image stay
-// interleaved).  wrank[v] = weak rows in front of position v, so the weak row at v is entry wrank[v] of the weak own
-// lists (which are aligned with w_off) and the strong row at v is entry v - wrank[v] of the strong ones.
-__global__ void own_fill_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ wrank,
-                                int64_t n, const uint32_t *__restrict__ q_of_det, uint32_t *__restrict__ own_w_q,
-                                uint16_t *__restrict__ own_w_m, uint16_t *__restrict__ own_w_c, uint32_t *__restrict__ own_s_q,
-                                uint16_t *__restrict__ own_s_m, uint16_t *__restrict__ own_s_c, uint32_t *__restrict__ ownpos) {
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n) return;
-    const uint32_t u = order[v];
-    if (u < d.Dw) {
-        const uint32_t pos = wrank[v];
-        own_w_q[pos] = q_of_det[u]; own_w_m[pos] = d.w_tp[u]; own_w_c[pos] = (uint16_t)d.w_cls[u];
-        ownpos[u] = pos;
-    } else {
-        const uint32_t pos = (uint32_t)v - wrank[v];
-        own_s_q[pos] = q_of_det[u]; own_s_m[pos] = d.s_tp[u - d.Dw]; own_s_c[pos] = (uint16_t)d.s_cls[u - d.Dw];
-        ownpos[u] = pos;
+// Own lists: the rows of one image and detector in (class, conf) order, i.e. ascending by their position in the
+// global order.  An image has a few hundred rows at most in practice, so one warp ranks them by counting (every
+// lane compares its rows with all rows of the image; the loads are warp-uniform) instead of a dataset-wide
+// regrouping sort.  Lists are aligned with w_off / s_off; ownpos remembers each row's entry.
+__global__ void own_lists_kernel(const Dets d, const int64_t *__restrict__ w_off, const int64_t *__restrict__ s_off, int64_t M,
+                                 const uint32_t *__restrict__ pos_of_det, const uint32_t *__restrict__ q_of_det,
+                                 uint32_t *__restrict__ own_w_q, uint16_t *__restrict__ own_w_m, uint16_t *__restrict__ own_w_c,
+                                 uint32_t *__restrict__ own_s_q, uint16_t *__restrict__ own_s_m, uint16_t *__restrict__ own_s_c,
+                                 uint32_t *__restrict__ ownpos) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= 2 * M) return;
+    const int lane = threadIdx.x & 31;
+    const bool strong = w >= M;
+    const int64_t im = strong ? w - M : w;
+    const int64_t *off = strong ? s_off : w_off;
+    const int64_t a = off[im];
+    const int n = (int)(off[im + 1] - a);
+    const uint32_t u0 = (uint32_t)(strong ? d.Dw + a : a);
+    const uint32_t *pos = pos_of_det + u0;
+    for (int r = lane; r < n; r += 32) {
+        const uint32_t mine = pos[r];
+        int rank = 0;
+        for (int k = 0; k < n; ++k) rank += pos[k] < mine;
+        const int64_t at = a + rank;
+        const uint32_t u = u0 + r;
+        if (strong) {
+            own_s_q[at] = q_of_det[u]; own_s_m[at] = d.s_tp[a + r]; own_s_c[at] = (uint16_t)d.s_cls[a + r];
+        } else {
+            own_w_q[at] = q_of_det[u]; own_w_m[at] = d.w_tp[a + r]; own_w_c[at] = (uint16_t)d.w_cls[a + r];
+        }
+        ownpos[u] = (uint32_t)at;
     }
 }
 
@@ -240,15 +255,15 @@ __global__ void batch_query_offsets_kernel(const uint2 *__restrict__ bq, const i
     bqoff[k] = (uint32_t)lo;
 }
 
-// r-th label in class order -> its slot of the padded label stream
-__global__ void place_labels_kernel(const uint32_t *__restrict__ lorder, const int32_t *__restrict__ l_cls,
-                                    const uint32_t *__restrict__ img_l, int64_t n, const uint32_t *__restrict__ cls_off,
-                                    const uint32_t *__restrict__ pad_off, uint32_t *__restrict__ slot_img) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const uint32_t g = lorder[r];
+// Labels into the padded class-major label stream.  Only the grouping by class matters (the label walk counts
+// members per class), so a label takes the next free slot of its class; no sort.
+__global__ void place_labels_kernel(const int32_t *__restrict__ l_cls, const uint32_t *__restrict__ img_l, int64_t n,
+                                    const uint32_t *__restrict__ pad_off, uint32_t *__restrict__ cursor,
+                                    uint32_t *__restrict__ slot_img) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
     const int c = l_cls[g];
-    slot_img[pad_off[c] + ((uint32_t)r - cls_off[c])] = img_l[g];
+    slot_img[pad_off[c] + atomicAdd(&cursor[c], 1u)] = img_l[g];
 }
 
 static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
@@ -409,7 +424,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     ORIE_TRY(B.keep(A));
 
     uint64_t *keys, *keys_tmp;
-    uint32_t *vtmp, *img_all, *img_l, *order, *ord_img, *ord_bat, *rank_img, *lorder, *meta, *wpre, *q_of_det, *ownpos, *d_total;
+    uint32_t *vtmp, *img_all, *img_l, *order, *ord_bat, *pos_of_det, *lcursor, *meta, *wpre, *q_of_det, *ownpos, *d_total;
     uint16_t *own_w_c, *own_s_c;
     char *scratch;
     A.add(&keys, n);
@@ -418,10 +433,9 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&img_all, n);
     A.add(&img_l, G);
     A.add(&order, n);
-    A.add(&ord_img, n);
     A.add(&ord_bat, n);
-    A.add(&rank_img, n);
-    A.add(&lorder, G);
+    A.add(&pos_of_det, n);
+    A.add(&lcursor, C);
     A.add(&meta, 3 * C + 1);
     A.add(&wpre, n);
     A.add(&q_of_det, n);
@@ -437,8 +451,9 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     ORIE_CUDA(cudaMemcpyAsync(ix->s_off, s_off, (size_t)(M + 1) * 8, cudaMemcpyDeviceToDevice, st));
     ORIE_CUDA(cudaMemsetAsync(meta, 0, (size_t)(3 * C + 1) * 4, st));
     ORIE_CUDA(cudaMemsetAsync(ix->gtcnt, 0, (size_t)(M * C) * 4, st));
+    ORIE_CUDA(cudaMemsetAsync(lcursor, 0, (size_t)C * 4, st));
 
-    const int cbits = bits_for(C), ibits = bits_for(M), bbits = bits_for(ix->nbatch);
+    const int cbits = bits_for(C), bbits = bits_for(ix->nbatch);
 
     // ---- prep: images of rows, confidence keys, class histograms, ground-truth counts, validation
     {
@@ -462,28 +477,14 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         ORIE_TRY(sort_add_passes(&j, kDigitKey, 0, 64));
         ORIE_TRY(sort_add_passes(&j, kDigitClass, 0, cbits));
         ORIE_TRY(sort_run(j, sort_blocks, scratch, st));
-        // the same order regrouped by image (the rank epilogue separates weak from strong rows, which saves the
-        // detector bit of the key) and by 32-image batch (weak and strong rows stay interleaved)
+        // the same order regrouped by 32-image batch: the per-batch query lists of the walk (weak and strong rows
+        // stay interleaved, ascending by slot)
         SortJob r;
         r.n = n;
-        r.vals_in = order; r.vals_a = ord_img; r.vals_b = vtmp;
+        r.vals_in = order; r.vals_a = ord_bat; r.vals_b = vtmp;
         r.img = img_all;
-        r.rank_out = rank_img; r.rank_split = (uint32_t)Dw;
-        ORIE_TRY(sort_add_passes(&r, kDigitImage, 0, ibits));
-        ORIE_TRY(sort_run(r, sort_blocks, scratch, st));
-        r.npass = 0;
-        r.vals_a = ord_bat;
-        r.rank_out = nullptr;
         ORIE_TRY(sort_add_passes(&r, kDigitBatch, 0, bbits));
         ORIE_TRY(sort_run(r, sort_blocks, scratch, st));
-    }
-    if (G) {
-        SortJob j;
-        j.n = G;
-        j.vals_a = lorder; j.vals_b = vtmp;
-        j.cls_lo = l_cls;
-        ORIE_TRY(sort_add_passes(&j, kDigitClass, 0, cbits));
-        ORIE_TRY(sort_run(j, sort_blocks, scratch, st));
     }
 
     // ---- host: class counts -> padded layouts and segment tables
@@ -524,10 +525,9 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     }
     for (int64_t c = 0; c < C; ++c) cls_order[c] = (int32_t)c;
     std::stable_sort(cls_order.begin(), cls_order.end(), [&](int32_t a, int32_t b) { return h_hist[a] > h_hist[b]; });
-    uint32_t *d_cls_off, *d_pad_off, *d_lcls_off, *d_lpad_off, *d_tables;
+    uint32_t *d_cls_off, *d_pad_off, *d_lpad_off, *d_tables;
     tab.add(&d_cls_off, LD.cls_off);
     tab.add(&d_pad_off, LD.pad_off);
-    tab.add(&d_lcls_off, LL.cls_off);
     tab.add(&d_lpad_off, LL.pad_off);
     tab.add(&ix->seg_chunk0, LD.seg_chunk0);
     tab.add(&ix->seg_nch, LD.seg_nch);
@@ -556,7 +556,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     if (tp_ready) ORIE_CUDA(cudaStreamWaitEvent(st, tp_ready, 0));     // first reader of the true-positive masks
     if (n) {
         place_slots_kernel<<<grid_for(n), 256, 0, st>>>(dets, order, wpre, img_all, n, d_cls_off, d_pad_off, ix->slot_img,
-                                                      ix->slot_tp, q_of_det);
+                                                      ix->slot_tp, q_of_det, pos_of_det);
         ORIE_LAUNCH_CHECK();
     }
 
@@ -577,8 +577,8 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
 
     // ---- own lists (image-major) and batch query lists (batch-major), both detectors in one pass each
     if (n) {
-        own_fill_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_img, rank_img, n, q_of_det, ix->own_w_q, ix->own_w_m, own_w_c,
-                                                   ix->own_s_q, ix->own_s_m, own_s_c, ownpos);
+        own_lists_kernel<<<grid_for(2 * M * 32), 256, 0, st>>>(dets, ix->w_off, ix->s_off, M, pos_of_det, q_of_det, ix->own_w_q,
+                                                             ix->own_w_m, own_w_c, ix->own_s_q, ix->own_s_m, own_s_c, ownpos);
         ORIE_LAUNCH_CHECK();
         batch_query_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_bat, img_all, n, q_of_det, ownpos, ix->bq);
         ORIE_LAUNCH_CHECK();
@@ -592,7 +592,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
 
     // ---- label stream
     if (G) {
-        place_labels_kernel<<<grid_for(G), 256, 0, st>>>(lorder, l_cls, img_l, G, d_lcls_off, d_lpad_off, ix->lab_slot_img);
+        place_labels_kernel<<<grid_for(G), 256, 0, st>>>(l_cls, img_l, G, d_lpad_off, lcursor, ix->lab_slot_img);
         ORIE_LAUNCH_CHECK();
     }
     ORIE_CUDA(cudaStreamSynchronize(st));

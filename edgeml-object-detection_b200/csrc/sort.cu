@@ -3,8 +3,8 @@
 //
 // The sort is the engine's "sort by (class, confidence)" — done ONCE per dataset
 // instead of once per target as lib/metrics.py:101 does (np.argsort(-conf) inside
-// every ap_per_class call) — and the two regroupings of that order by image and
-// by 32-image batch (index.cu).
+// every ap_per_class call) — and the regrouping of that order by 32-image batch
+// (index.cu).
 //
 // One CTA per SM owns a contiguous range of the items.  Per 8-bit pass:
 //   A  digit histogram of the CTA's range (shared-memory atomics) -> table[cta][digit]
@@ -16,8 +16,8 @@
 //      per-warp digit counters carry ranks across steps, warps and tiles
 //      -- grid barrier --
 // The digit of a pass is either 8 bits of a 64-bit key or a function of the item's
-// value (class / image / batch of the detection id), so the regrouping sorts move
-// 4-byte values only and need no re-keying kernels.
+// value (class / batch of the detection id), so the regrouping sort moves 4-byte
+// values only and needs no re-keying kernel.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -41,8 +41,6 @@ __device__ __forceinline__ uint32_t digit_source(const SortJob &j, int kind, uin
     switch (kind) {
     case kDigitClass:
         return (uint32_t)(u < j.split ? __ldg(j.cls_lo + u) : __ldg(j.cls_hi + (u - j.split)));
-    case kDigitImage:
-        return __ldg(j.img + u);
     default:  // kDigitBatch
         return __ldg(j.img + u) >> 5;
     }
