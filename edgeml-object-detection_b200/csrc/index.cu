@@ -91,179 +91,178 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepArgs a) {
         if (bins[i]) atomicAdd(&a.hist[i], bins[i]);
 }
 
-// padding slots: image M (never a member), no true positive
-__global__ void init_slots_kernel(uint32_t *__restrict__ slot_img, uint16_t *__restrict__ slot_tp, int64_t P,
-                                  uint32_t *__restrict__ lab_slot_img, int64_t PL, uint32_t M) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += stride) {
-        slot_img[k] = M;
-        slot_tp[k] = 0;
-    }
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < PL; k += stride) lab_slot_img[k] = M;
-}
+// ----------------------------------------------------------------------------
+// Everything after the host has laid out the classes, in ONE cooperative launch (five phases separated by grid
+// barriers; eight dependent launches of a few microseconds each before, whose enqueue cost exceeded their run time):
+//   1  padding slots of both streams: image M (never a member), no true positive
+//   2  position v of the combined (class, conf desc) order -> slot (weak) / insertion slot (strong)
+//      [wpre[v] = weak detections sorted before v]; labels into the class-major label stream (only the grouping by
+//      class matters — the label walk counts members per class — so a label takes the next free slot of its class)
+//   3  event counts per CTA range of chunks (event = slot holding a true positive);
+//      own lists: the rows of one image and detector in (class, conf) order, i.e. ascending by their position in the
+//      global order — an image has a few hundred rows at most in practice, so one warp ranks them by counting instead
+//      of a dataset-wide regrouping sort — and the class-start table of the list: cs[img][c] = first entry with
+//      class >= c, c in [0, C]
+//   4  evbase = events in front of every chunk (exclusive scan), their total; per-batch query list: position v of the
+//      batch-major order IS the entry, ascending by slot with weak and strong rows interleaved
+//   5  each segment's first event; bqoff[b][s] = first query of batch b with slot >= first slot of segment s
+// Arrays written in one phase and read in a later one are read with __ldcg (L2), never through the read-only path.
+// ----------------------------------------------------------------------------
+struct PostArgs {
+    Dets d;
+    int64_t n, M, C, G, P, PL, nchunks, S, nbatch, ev_per;
+    const uint32_t *order, *wpre, *img_all, *ord_bat, *img_l;
+    const int32_t *l_cls, *seg_chunk0;
+    const uint32_t *cls_off, *pad_off, *lpad_off;
+    const int64_t *w_off, *s_off;
+    uint32_t *lcursor;
+    uint32_t *slot_img, *lab_slot_img;
+    uint16_t *slot_tp;
+    uint32_t *q_of_det, *pos_of_det, *ownpos;
+    uint32_t *own_w_q, *own_s_q;
+    uint16_t *own_w_m, *own_s_m, *own_w_c, *own_s_c, *own_w_cs, *own_s_cs;
+    uint2 *bq;
+    uint32_t *bqoff, *evbase, *seg_ev0, *table, *total_out;
+    unsigned *bar;
+};
+constexpr int kPostThreads = 256;
+constexpr int kPostWarps = kPostThreads / 32;
+constexpr int kRankStage = 256;          // rows of an image staged in shared memory for the ranking
 
-// position v of the combined (class, conf desc) order -> slot (weak) / insertion slot (strong).
-// wpre[v] = number of weak detections sorted before v.
-__global__ void place_slots_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ wpre,
-                                   const uint32_t *__restrict__ img_all, int64_t n, const uint32_t *__restrict__ cls_off,
-                                   const uint32_t *__restrict__ pad_off, uint32_t *__restrict__ slot_img,
-                                   uint16_t *__restrict__ slot_tp, uint32_t *__restrict__ q_of_det,
-                                   uint32_t *__restrict__ pos_of_det) {
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n) return;
-    const uint32_t u = order[v];
-    const int c = d.cls(u);
-    const uint32_t slot = pad_off[c] + (wpre[v] - cls_off[c]);
-    q_of_det[u] = slot;       // weak: its own slot; strong: the slot it would be inserted in front of
-    pos_of_det[u] = (uint32_t)v;
-    if (u < d.Dw) {
-        slot_img[slot] = img_all[u];
-        slot_tp[slot] = d.w_tp[u];
-    }
-}
-
-// ---- event counts in one cooperative launch: events (slots holding a true positive) in front of every chunk
-// (evbase = exclusive scan of the per-chunk counts), their total, and each segment's first event.
-constexpr int kEvThreads = 512;
-__global__ void __launch_bounds__(kEvThreads)
-events_kernel(const uint16_t *__restrict__ slot_tp, int64_t nchunks, int64_t per, uint32_t *evbase,
-              const int32_t *__restrict__ seg_chunk0, int64_t S, uint32_t *__restrict__ seg_ev0, uint32_t *table,
-              unsigned *bar, uint32_t *__restrict__ total_out) {
-    __shared__ uint32_t ws[kEvThreads / 32];
+__global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
+    __shared__ uint32_t ws[kPostWarps];
+    __shared__ uint32_t staged[kPostWarps][kRankStage];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t gtid = (int64_t)blockIdx.x * kPostThreads + threadIdx.x;
+    const int64_t gsize = (int64_t)gridDim.x * kPostThreads;
+    const int64_t gwarp = gtid >> 5, nwarps = gsize >> 5;
     unsigned epoch = 0;
-    const int64_t c0 = (int64_t)blockIdx.x * per, c1 = c0 + per < nchunks ? c0 + per : nchunks;
-    const int64_t cw = (per + kEvThreads / 32 - 1) / (kEvThreads / 32);
+
+    // ---- 1
+    for (int64_t k = gtid; k < a.P; k += gsize) {
+        a.slot_img[k] = (uint32_t)a.M;
+        a.slot_tp[k] = 0;
+    }
+    for (int64_t k = gtid; k < a.PL; k += gsize) a.lab_slot_img[k] = (uint32_t)a.M;
+    grid_sync(a.bar, epoch);
+
+    // ---- 2
+    for (int64_t v = gtid; v < a.n; v += gsize) {
+        const uint32_t u = a.order[v];
+        const int c = a.d.cls(u);
+        const uint32_t slot = a.pad_off[c] + (a.wpre[v] - a.cls_off[c]);
+        a.q_of_det[u] = slot;       // weak: its own slot; strong: the slot it would be inserted in front of
+        a.pos_of_det[u] = (uint32_t)v;
+        if (u < a.d.Dw) {
+            a.slot_img[slot] = a.img_all[u];
+            a.slot_tp[slot] = a.d.w_tp[u];
+        }
+    }
+    for (int64_t g = gtid; g < a.G; g += gsize) {
+        const int c = a.l_cls[g];
+        a.lab_slot_img[a.lpad_off[c] + atomicAdd(&a.lcursor[c], 1u)] = a.img_l[g];
+    }
+    grid_sync(a.bar, epoch);
+
+    // ---- 3: events of this CTA's chunk range, split over its warps
+    const int64_t c0 = (int64_t)blockIdx.x * a.ev_per, c1 = c0 + a.ev_per < a.nchunks ? c0 + a.ev_per : a.nchunks;
+    const int64_t cw = (a.ev_per + kPostWarps - 1) / kPostWarps;
     const int64_t w0 = c0 + warp * cw, w1 = w0 + cw < c1 ? w0 + cw : c1;
     uint32_t mine = 0;
-    for (int64_t ch = w0; ch < w1; ++ch) {
-        mine += __popc(__ballot_sync(kFull, slot_tp[ch * 32 + lane] != 0));
-    }
+    for (int64_t ch = w0; ch < w1; ++ch) mine += __popc(__ballot_sync(kFull, __ldcg(a.slot_tp + ch * 32 + lane) != 0));
     uint32_t cta_total;
-    const uint32_t excl = block_exclusive_scan<kEvThreads>(lane == 0 ? mine : 0u, ws, &cta_total);
+    const uint32_t excl = block_exclusive_scan<kPostThreads>(lane == 0 ? mine : 0u, ws, &cta_total);
     const uint32_t warp_base = __shfl_sync(kFull, excl, 0);
-    if (threadIdx.x == 0) __stcg(table + blockIdx.x, cta_total);
-    grid_sync(bar, epoch);
-    uint32_t before = 0, all = 0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += kEvThreads) {
-        const uint32_t v = __ldcg(table + b);
-        all += v;
-        before += b < (int)blockIdx.x ? v : 0u;
+    if (threadIdx.x == 0) __stcg(a.table + blockIdx.x, cta_total);
+    // own lists and their class-start tables: one warp per (detector, image)
+    for (int64_t w = gwarp; w < 2 * a.M; w += nwarps) {
+        const bool strong = w >= a.M;
+        const int64_t im = strong ? w - a.M : w;
+        const int64_t *off = strong ? a.s_off : a.w_off;
+        const int64_t r0 = off[im];
+        const int n = (int)(off[im + 1] - r0);
+        const uint32_t u0 = (uint32_t)(strong ? a.d.Dw + r0 : r0);
+        const uint32_t *pos = a.pos_of_det + u0;
+        uint32_t *own_q = strong ? a.own_s_q : a.own_w_q;
+        uint16_t *own_m = strong ? a.own_s_m : a.own_w_m, *own_c = strong ? a.own_s_c : a.own_w_c;
+        const uint16_t *tp = strong ? a.d.s_tp : a.d.w_tp;
+        const int32_t *cls = strong ? a.d.s_cls : a.d.w_cls;
+        const bool fits = n <= kRankStage;
+        __syncwarp();
+        if (fits)
+            for (int k = lane; k < n; k += 32) staged[warp][k] = __ldcg(pos + k);
+        __syncwarp();
+        for (int r = lane; r < n; r += 32) {
+            const uint32_t me = fits ? staged[warp][r] : __ldcg(pos + r);
+            int rank = 0;
+            if (fits) {
+                for (int k = 0; k < n; ++k) rank += staged[warp][k] < me;
+            } else {
+                for (int k = 0; k < n; ++k) rank += __ldcg(pos + k) < me;
+            }
+            const int64_t at = r0 + rank;
+            own_q[at] = __ldcg(a.q_of_det + u0 + r);
+            own_m[at] = tp[r0 + r];
+            own_c[at] = (uint16_t)cls[r0 + r];
+            a.ownpos[u0 + r] = (uint32_t)at;
+        }
+        __syncwarp();                      // the list of this image is complete (written by this warp)
+        const uint16_t *list = own_c + r0;
+        uint16_t *row = (strong ? a.own_s_cs : a.own_w_cs) + im * (a.C + 1);
+        for (int c = lane; c <= a.C; c += 32) {
+            int lo = 0, hi = n;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((int)list[mid] < c) lo = mid + 1; else hi = mid;
+            }
+            row[c] = (uint16_t)lo;
+        }
     }
-    uint32_t carry, grand;
-    block_exclusive_scan<kEvThreads>(before, ws, &carry);
-    block_exclusive_scan<kEvThreads>(all, ws, &grand);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *total_out = grand;
-    uint32_t run = carry + warp_base;
-    for (int64_t ch = w0; ch < w1; ++ch) {
-        const unsigned b = __ballot_sync(kFull, slot_tp[ch * 32 + lane] != 0);
-        if (lane == 0) evbase[ch] = run;
-        run += __popc(b);
-    }
-    grid_sync(bar, epoch);
-    for (int64_t s = (int64_t)blockIdx.x * kEvThreads + threadIdx.x; s < S; s += (int64_t)gridDim.x * kEvThreads)
-        seg_ev0[s] = __ldcg(evbase + seg_chunk0[s]);
-}
+    grid_sync(a.bar, epoch);
 
-// Own lists: the rows of one image and detector in (class, conf) order, i.e. ascending by their position in the
-// global order.  An image has a few hundred rows at most in practice, so one warp ranks them by counting (every
-// lane compares its rows with all rows of the image; the loads are warp-uniform) instead of a dataset-wide
-// regrouping sort.  Lists are aligned with w_off / s_off; ownpos remembers each row's entry.
-__global__ void own_lists_kernel(const Dets d, const int64_t *__restrict__ w_off, const int64_t *__restrict__ s_off, int64_t M,
-                                 const uint32_t *__restrict__ pos_of_det, const uint32_t *__restrict__ q_of_det,
-                                 uint32_t *__restrict__ own_w_q, uint16_t *__restrict__ own_w_m, uint16_t *__restrict__ own_w_c,
-                                 uint32_t *__restrict__ own_s_q, uint16_t *__restrict__ own_s_m, uint16_t *__restrict__ own_s_c,
-                                 uint32_t *__restrict__ ownpos) {
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= 2 * M) return;
-    const int lane = threadIdx.x & 31;
-    const bool strong = w >= M;
-    const int64_t im = strong ? w - M : w;
-    const int64_t *off = strong ? s_off : w_off;
-    const int64_t a = off[im];
-    const int n = (int)(off[im + 1] - a);
-    const uint32_t u0 = (uint32_t)(strong ? d.Dw + a : a);
-    const uint32_t *pos = pos_of_det + u0;
-    for (int r = lane; r < n; r += 32) {
-        const uint32_t mine = pos[r];
-        int rank = 0;
-        for (int k = 0; k < n; ++k) rank += pos[k] < mine;
-        const int64_t at = a + rank;
-        const uint32_t u = u0 + r;
-        if (strong) {
-            own_s_q[at] = q_of_det[u]; own_s_m[at] = d.s_tp[a + r]; own_s_c[at] = (uint16_t)d.s_cls[a + r];
+    // ---- 4
+    {
+        uint32_t before = 0, all = 0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += kPostThreads) {
+            const uint32_t v = __ldcg(a.table + b);
+            all += v;
+            before += b < (int)blockIdx.x ? v : 0u;
+        }
+        uint32_t carry, grand;
+        block_exclusive_scan<kPostThreads>(before, ws, &carry);
+        block_exclusive_scan<kPostThreads>(all, ws, &grand);
+        if (blockIdx.x == 0 && threadIdx.x == 0) *a.total_out = grand;
+        uint32_t run = carry + warp_base;
+        for (int64_t ch = w0; ch < w1; ++ch) {
+            const unsigned b = __ballot_sync(kFull, __ldcg(a.slot_tp + ch * 32 + lane) != 0);
+            if (lane == 0) a.evbase[ch] = run;
+            run += __popc(b);
+        }
+    }
+    for (int64_t v = gtid; v < a.n; v += gsize) {
+        const uint32_t u = a.ord_bat[v];
+        a.bq[v] = make_uint2(__ldcg(a.q_of_det + u) | (u >= a.d.Dw ? 0x80000000u : 0u),
+                             ((a.img_all[u] & 31u) << 27) | __ldcg(a.ownpos + u));
+    }
+    grid_sync(a.bar, epoch);
+
+    // ---- 5
+    for (int64_t s = gtid; s < a.S; s += gsize) a.seg_ev0[s] = __ldcg(a.evbase + a.seg_chunk0[s]);
+    for (int64_t k = gtid; k < a.nbatch * (a.S + 1); k += gsize) {
+        const int64_t b = k / (a.S + 1), s = k % (a.S + 1);
+        const int64_t i0 = b * 32 < a.M ? b * 32 : a.M, i1 = (b + 1) * 32 < a.M ? (b + 1) * 32 : a.M;
+        int64_t lo = a.w_off[i0] + a.s_off[i0], hi = a.w_off[i1] + a.s_off[i1];
+        if (s < a.S) {
+            const uint32_t slot0 = (uint32_t)a.seg_chunk0[s] * 32u;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if ((__ldcg(&a.bq[mid].x) & 0x7fffffffu) < slot0) lo = mid + 1; else hi = mid;
+            }
         } else {
-            own_w_q[at] = q_of_det[u]; own_w_m[at] = d.w_tp[a + r]; own_w_c[at] = (uint16_t)d.w_cls[a + r];
+            lo = hi;
         }
-        ownpos[u] = (uint32_t)at;
+        a.bqoff[k] = (uint32_t)lo;
     }
-}
-
-// class start table of every image's own list (ascending by class): cs[img][c] = first local index with
-// class >= c, c in [0, C].  One warp per (detector, image); every entry of the row is written.
-__global__ void own_class_start_kernel(const uint16_t *__restrict__ own_w_c, const int64_t *__restrict__ w_off,
-                                       uint16_t *__restrict__ w_cs, const uint16_t *__restrict__ own_s_c,
-                                       const int64_t *__restrict__ s_off, uint16_t *__restrict__ s_cs, int64_t M, int64_t C) {
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= 2 * M) return;
-    const int lane = threadIdx.x & 31;
-    const bool strong = w >= M;
-    const int64_t im = strong ? w - M : w;
-    const int64_t *off = strong ? s_off : w_off;
-    const uint16_t *list = (strong ? own_s_c : own_w_c) + off[im];
-    const int len = (int)(off[im + 1] - off[im]);
-    uint16_t *row = (strong ? s_cs : w_cs) + im * (C + 1);
-    for (int c = lane; c <= C; c += 32) {
-        int lo = 0, hi = len;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((int)list[mid] < c) lo = mid + 1; else hi = mid;
-        }
-        row[c] = (uint16_t)lo;
-    }
-}
-
-// Batch-major order (the (class, conf) order stably regrouped by 32-image batch): position v IS the entry of the
-// batch's query list, which is therefore ascending by query slot with weak and strong rows interleaved.
-__global__ void batch_query_kernel(const Dets d, const uint32_t *__restrict__ order, const uint32_t *__restrict__ img_all,
-                                   int64_t n, const uint32_t *__restrict__ q_of_det, const uint32_t *__restrict__ ownpos,
-                                   uint2 *__restrict__ bq) {
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n) return;
-    const uint32_t u = order[v];
-    bq[v] = make_uint2(q_of_det[u] | (u >= d.Dw ? 0x80000000u : 0u), ((img_all[u] & 31u) << 27) | ownpos[u]);
-}
-
-// bqoff[b][s] = first entry of batch b with q >= first slot of segment s  (s == S: end of the batch)
-__global__ void batch_query_offsets_kernel(const uint2 *__restrict__ bq, const int64_t *__restrict__ w_off,
-                                           const int64_t *__restrict__ s_off, uint32_t *__restrict__ bqoff, int64_t M,
-                                           int64_t nbatch, const int32_t *__restrict__ seg_chunk0, int64_t S) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nbatch * (S + 1)) return;
-    const int64_t b = k / (S + 1), s = k % (S + 1);
-    const int64_t i0 = b * 32 < M ? b * 32 : M, i1 = (b + 1) * 32 < M ? (b + 1) * 32 : M;
-    int64_t lo = w_off[i0] + s_off[i0], hi = w_off[i1] + s_off[i1];
-    if (s < S) {
-        const uint32_t slot0 = (uint32_t)seg_chunk0[s] * 32u;
-        while (lo < hi) {
-            int64_t mid = (lo + hi) >> 1;
-            if ((bq[mid].x & 0x7fffffffu) < slot0) lo = mid + 1; else hi = mid;
-        }
-    } else {
-        lo = hi;
-    }
-    bqoff[k] = (uint32_t)lo;
-}
-
-// Labels into the padded class-major label stream.  Only the grouping by class matters (the label walk counts
-// members per class), so a label takes the next free slot of its class; no sort.
-__global__ void place_labels_kernel(const int32_t *__restrict__ l_cls, const uint32_t *__restrict__ img_l, int64_t n,
-                                    const uint32_t *__restrict__ pad_off, uint32_t *__restrict__ cursor,
-                                    uint32_t *__restrict__ slot_img) {
-    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n) return;
-    const int c = l_cls[g];
-    slot_img[pad_off[c] + atomicAdd(&cursor[c], 1u)] = img_l[g];
 }
 
 static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
@@ -405,9 +404,9 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     const int64_t n = Dw + Ds;
     const int64_t Nmax = std::max<int64_t>(std::max(n, G), 1);
     const Dets dets{Dw, Ds, w_cls, s_cls, w_conf, s_conf, w_tp, s_tp};
-    int sort_blocks = 0, ev_blocks = 0;
+    int sort_blocks = 0, post_blocks = 0;
     ORIE_TRY(sort_max_blocks(&sort_blocks));
-    ORIE_TRY(coop_max_blocks(events_kernel, kEvThreads, 0, &ev_blocks));
+    ORIE_TRY(coop_max_blocks(post_kernel, kPostThreads, 0, &post_blocks));
 
     // ---- first part of the index (sizes known up front) and the temporaries, one allocation each
     Arena A;
@@ -443,7 +442,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&own_w_c, Dw);
     A.add(&own_s_c, Ds);
     A.add(&d_total, 1);
-    A.add(&scratch, (int64_t)std::max(sort_scratch_bytes(sort_blocks), (size_t)ev_blocks * 4 + 256));
+    A.add(&scratch, (int64_t)std::max(sort_scratch_bytes(sort_blocks), (size_t)post_blocks * 4 + 256));
     ORIE_TRY(A.commit(st, &B.temp_base, nullptr));
     int32_t *status = (int32_t *)(meta + 3 * C);
 
@@ -550,50 +549,34 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     ORIE_CUDA(cudaMemcpyAsync(d_tables, tab.words.data(), tab.words.size() * 4, cudaMemcpyHostToDevice, st));
     // tab.words stays alive until the end of this function, which ends with a stream synchronisation
 
-    // ---- slots, strong insertion slots
-    init_slots_kernel<<<148 * 4, 256, 0, st>>>(ix->slot_img, ix->slot_tp, ix->P, ix->lab_slot_img, ix->PL, (uint32_t)M);
-    ORIE_LAUNCH_CHECK();
+    // ---- everything else in one cooperative launch (post_kernel)
     if (tp_ready) ORIE_CUDA(cudaStreamWaitEvent(st, tp_ready, 0));     // first reader of the true-positive masks
-    if (n) {
-        place_slots_kernel<<<grid_for(n), 256, 0, st>>>(dets, order, wpre, img_all, n, d_cls_off, d_pad_off, ix->slot_img,
-                                                      ix->slot_tp, q_of_det, pos_of_det);
-        ORIE_LAUNCH_CHECK();
-    }
-
-    // ---- events (the total is read back together with the final synchronisation)
     {
-        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ev_blocks, ceil_div(ix->nchunks, 4 * (kEvThreads / 32))));
-        int64_t per = ceil_div(std::max<int64_t>(ix->nchunks, 1), blocks);
-        unsigned *bar = (unsigned *)scratch;
-        uint32_t *table = (uint32_t *)(scratch + 256);
-        ORIE_CUDA(cudaMemsetAsync(bar, 0, 4, st));
-        const uint16_t *tp_c = ix->slot_tp;
-        int64_t nch = ix->nchunks, S = ix->S;
-        void *args[] = {&tp_c, &nch, &per, &ix->evbase, &ix->seg_chunk0, &S, &ix->seg_ev0, &table, &bar, &d_total};
-        ORIE_CUDA(cudaLaunchCooperativeKernel((const void *)events_kernel, dim3(blocks), dim3(kEvThreads), args, 0, st));
+        PostArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        pa.d = dets;
+        pa.n = n; pa.M = M; pa.C = C; pa.G = G; pa.P = ix->P; pa.PL = ix->PL; pa.nchunks = ix->nchunks; pa.S = ix->S;
+        pa.nbatch = ix->nbatch;
+        pa.order = order; pa.wpre = wpre; pa.img_all = img_all; pa.ord_bat = ord_bat; pa.img_l = img_l;
+        pa.l_cls = l_cls; pa.seg_chunk0 = ix->seg_chunk0;
+        pa.cls_off = d_cls_off; pa.pad_off = d_pad_off; pa.lpad_off = d_lpad_off;
+        pa.w_off = ix->w_off; pa.s_off = ix->s_off;
+        pa.lcursor = lcursor;
+        pa.slot_img = ix->slot_img; pa.lab_slot_img = ix->lab_slot_img; pa.slot_tp = ix->slot_tp;
+        pa.q_of_det = q_of_det; pa.pos_of_det = pos_of_det; pa.ownpos = ownpos;
+        pa.own_w_q = ix->own_w_q; pa.own_s_q = ix->own_s_q; pa.own_w_m = ix->own_w_m; pa.own_s_m = ix->own_s_m;
+        pa.own_w_c = own_w_c; pa.own_s_c = own_s_c; pa.own_w_cs = ix->own_w_cs; pa.own_s_cs = ix->own_s_cs;
+        pa.bq = ix->bq; pa.bqoff = ix->bqoff; pa.evbase = ix->evbase; pa.seg_ev0 = ix->seg_ev0;
+        pa.bar = (unsigned *)scratch;
+        pa.table = (uint32_t *)(scratch + 256);
+        pa.total_out = d_total;
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(post_blocks, ceil_div(std::max(n, ix->P), kPostThreads)));
+        pa.ev_per = ceil_div(std::max<int64_t>(ix->nchunks, 1), blocks);
+        ORIE_CUDA(cudaMemsetAsync(pa.bar, 0, 4, st));
+        void *args[] = {&pa};
+        ORIE_CUDA(cudaLaunchCooperativeKernel((const void *)post_kernel, dim3(blocks), dim3(kPostThreads), args, 0, st));
         ORIE_LAUNCH_CHECK();
         ORIE_CUDA(cudaMemcpyAsync(&h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
-    }
-
-    // ---- own lists (image-major) and batch query lists (batch-major), both detectors in one pass each
-    if (n) {
-        own_lists_kernel<<<grid_for(2 * M * 32), 256, 0, st>>>(dets, ix->w_off, ix->s_off, M, pos_of_det, q_of_det, ix->own_w_q,
-                                                             ix->own_w_m, own_w_c, ix->own_s_q, ix->own_s_m, own_s_c, ownpos);
-        ORIE_LAUNCH_CHECK();
-        batch_query_kernel<<<grid_for(n), 256, 0, st>>>(dets, ord_bat, img_all, n, q_of_det, ownpos, ix->bq);
-        ORIE_LAUNCH_CHECK();
-    }
-    own_class_start_kernel<<<grid_for(2 * M * 32), 256, 0, st>>>(own_w_c, ix->w_off, ix->own_w_cs, own_s_c, ix->s_off,
-                                                               ix->own_s_cs, M, C);
-    ORIE_LAUNCH_CHECK();
-    batch_query_offsets_kernel<<<grid_for(ix->nbatch * (ix->S + 1)), 256, 0, st>>>(ix->bq, ix->w_off, ix->s_off, ix->bqoff, M,
-                                                                                 ix->nbatch, ix->seg_chunk0, ix->S);
-    ORIE_LAUNCH_CHECK();
-
-    // ---- label stream
-    if (G) {
-        place_labels_kernel<<<grid_for(G), 256, 0, st>>>(l_cls, img_l, G, d_lpad_off, lcursor, ix->lab_slot_img);
-        ORIE_LAUNCH_CHECK();
     }
     ORIE_CUDA(cudaStreamSynchronize(st));
     ix->Ev = h_total;
