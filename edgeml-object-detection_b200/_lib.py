@@ -18,6 +18,7 @@ SYMBOLS = [
     "orie_index_build", "orie_index_destroy", "orie_index_info",
     "orie_ensemble_from_indices", "orie_ensemble_sample",
     "orie_reward_workspace_bytes", "orie_reward", "orie_reward_sums", "orie_reward_profile", "orie_launch_count",
+    "orie_rank_workspace_bytes", "orie_rank_normalize",
 ]
 
 
@@ -83,6 +84,10 @@ def load():
     lib.orie_reward_sums.restype = C.c_int
     lib.orie_reward_sums.argtypes = [vp, i64, i64, vp, i64, vp, C.c_size_t, vp, i32, vp]
     lib.orie_reward_profile.argtypes = [vp, i64, i64, vp, i64, vp, C.c_size_t, vp, vp, i32, vp, C.POINTER(C.c_float)]
+    lib.orie_rank_workspace_bytes.restype = C.c_size_t
+    lib.orie_rank_workspace_bytes.argtypes = [i64]
+    lib.orie_rank_normalize.restype = C.c_int
+    lib.orie_rank_normalize.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
     lib.orie_launch_count.restype = C.c_longlong
     lib.orie_launch_count.argtypes = []
     _LIB = lib

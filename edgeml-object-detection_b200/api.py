@@ -165,6 +165,35 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
     return reward, seconds, info
 
 
+def rank_normalize(reward, val_mask=None, device=None) -> np.ndarray:
+    """Rank-normalised rewards of one cross-validation fold, as ``regression.py:439-441`` computes them when
+    ``--normalize`` is set: train rows get ``(argsort(argsort(train)) + 1) / len(train)``, validation rows the share
+    of train rewards not above their own.  ``val_mask``: bool[M] (None = every row is a train row).  Runs on the GPU
+    (``orie_rank_normalize``); equal train rewards rank in row order."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("orie_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    r = torch.from_numpy(np.ascontiguousarray(reward, dtype=np.float64)).to(dev)
+    M = int(r.numel())
+    out = torch.empty(M, dtype=torch.float64, device=dev)
+    mask = None
+    if val_mask is not None:
+        vm = np.ascontiguousarray(val_mask, dtype=bool)
+        if vm.shape != (M,):
+            raise ValueError(f"val_mask must have shape ({M},), got {vm.shape}")
+        mask = torch.from_numpy(vm.view(np.uint8)).to(dev)
+    with torch.cuda.device(dev):
+        ws = torch.empty(int(lib.orie_rank_workspace_bytes(M)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.orie_rank_normalize(C.c_void_p(r.data_ptr()), C.c_void_p(mask.data_ptr() if mask is not None else 0), M,
+                                           C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out.cpu().numpy()
+
+
 def save_rewards(save_dir, method, num_ensemble, reward, seconds):
     """reward.py:90-92: ``orie{N}.npz`` (N as typed on the command line, not the
     clamped value) or ``dcsb.npz`` with keys ``reward`` and ``time``."""

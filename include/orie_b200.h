@@ -169,6 +169,18 @@ int orie_reward_profile(const orie_index_t *idx, int64_t t0, int64_t nt, const u
                         void *workspace, size_t workspace_bytes, double *reward, double *sums, int full,
                         orie_stream_t stream, float *kernel_ms_host);
 
+/*
+ * Rank normalisation of a reward vector for one cross-validation fold.  Replaces regression.py:439-441:
+ *   train rows (val_mask[i] == 0):  out[i] = (argsort(argsort(train)) + 1)[i] / len(train)
+ *   validation rows:                out[i] = sum(train <= reward[i]) / len(train)
+ * val_mask nullable (every row is a train row).  Equal train rewards rank in row order (upstream's argsort is
+ * unstable, so their order is machine-dependent there).  reward, out: f64[M]; val_mask: u8[M];
+ * workspace: orie_rank_workspace_bytes(M) bytes, 256-byte aligned.
+ */
+size_t orie_rank_workspace_bytes(int64_t M);
+int orie_rank_normalize(const double *reward, const uint8_t *val_mask, int64_t M, double *out,
+                        void *workspace, size_t workspace_bytes, orie_stream_t stream);
+
 /* Number of kernels this library has launched in this process (all threads). */
 long long orie_launch_count(void);
 
