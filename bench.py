@@ -8,7 +8,8 @@ One *step* = the whole hot path over the workload, from the packed dataset
 already resident in HBM to the reward vector: FP64 IoU + TP matching for both
 detectors, dataset index build (radix sort by class/confidence), device-side
 ensemble draw, membership walk, 101-point AP integration, (N+1)*dmAP, and for
-N>1 GPUs one NCCL all-gather of the per-rank reward slices.  ``value`` is
+N>1 GPUs one NCCL collective (all-reduce of per-target AP sums when the classes
+are sharded over the ranks, all-gather of reward slices when the targets are).  ``value`` is
 rewards (= target images) per second over the K timed steps (CUDA events per
 step, summed; max over ranks).  ``e2e`` is the same job through the public
 Python API starting from PINNED HOST buffers (H2D of the packed dataset and
@@ -435,7 +436,7 @@ def run_b200(args):
                    "iou_thresholds": T, "weak_dets": int(len(pk_all.w_cls)), "strong_dets": int(len(pk_all.s_cls)),
                    "labels": int(len(pk_all.l_cls)), "parallelism": (f"classes sharded over {world} gpus (every rank: all targets, its classes), one all-reduce of 3 doubles "
                                    f"per target" if by_class else f"targets sharded over {world} gpu(s), index replicated, one all-gather"),
-                   "step": "TP matching (2 detectors) + index build + ensemble draw + membership walk + AP + all-gather",
+                   "step": "TP matching (2 detectors) + index build + ensemble draw + membership walk + AP + collective",
                    "l2": "flushed between steps (256 MiB write, not timed)", "ensembles": "device-side Philox draw, seed per step",
                    "index": {k: info[k] for k in ("slots", "segments", "events", "seg_chunks", "class_groups")},
                    "phase_ms": {k: sum(v) / len(v) for k, v in phase_ms.items()}, "wall_s_timed_region": wall},

@@ -106,6 +106,12 @@ def test_shard_ranges_cover_the_targets_once():
             assert all(engine.shard_range(M, r, world)[1] <= per for r in range(world))
 
 
+def test_shard_mode_follows_the_dataset_size():
+    assert engine.pick_shard(5000) == "classes" and engine.pick_shard(28000) == "classes"
+    assert engine.pick_shard(50000) == "targets"
+    assert engine.pick_shard(50000, "classes") == "classes" and engine.pick_shard(10, "targets") == "targets"
+
+
 def test_c_abi_exports_every_declared_symbol():
     from orie_b200 import _lib
     header = open(os.path.join(ROOT, "include", "orie_b200.h")).read()
