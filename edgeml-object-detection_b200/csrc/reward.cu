@@ -450,8 +450,12 @@ ap_kernel(const ApParams p, const Grid101 grid) {
         const int c = p.cls_order[ci];          // classes of similar size share a warp
         uint32_t n_l = p.gtcnt[j * p.C + c];
         for (int ls = p.lcls_seg0[c]; ls < p.lcls_seg0[c + 1]; ++ls) n_l += p.totL[(int64_t)ls * p.ntp + tl];
-        if (n_l > 0) {
-            if (t == 0) has_gt = 1.0;
+        const uint16_t *wcs = p.own_w_cs + j * (p.C + 1) + c, *scs = p.own_s_cs + j * (p.C + 1) + c;
+        const int wa = wcs[0], wb = wcs[1], sa = scs[0], sb = scs[1];
+        // the target has no detection of this class from either detector: both variants are the same integral
+        const bool same = (wb == wa) && (sb == sa);
+        if (n_l > 0 && t == 0) has_gt = 1.0;
+        if (n_l > 0 && (FULL || !same)) {
             const int s0 = p.cls_seg0[c], s1 = p.cls_seg0[c + 1];
             const uint32_t *ev = p.ev + tl * p.Ev;
             const uint32_t *tot = p.tot + tl, *evcnt = p.evcnt + tl;
@@ -467,8 +471,6 @@ ap_kernel(const ApParams p, const Grid101 grid) {
                 }
                 for (; i < ne; ++i) K_ens += (e[i] >> (16 + t)) & 1u;
             }
-            const uint16_t *wcs = p.own_w_cs + j * (p.C + 1) + c, *scs = p.own_s_cs + j * (p.C + 1) + c;
-            const int wa = wcs[0], wb = wcs[1], sa = scs[0], sb = scs[1];
             const uint32_t *wq = p.own_w_q + p.w_off[j], *wcb = p.cb_w + p.w_off[j];
             const uint32_t *sq = p.own_s_q + p.s_off[j], *scb = p.cb_s + p.s_off[j];
             const uint16_t *wm = p.own_w_m + p.w_off[j], *sm = p.own_s_m + p.s_off[j];
@@ -478,10 +480,7 @@ ap_kernel(const ApParams p, const Grid101 grid) {
             ApVar vw, vs;
             vw.init(cw, cwx, ge, K_w, n_ens + (uint32_t)(wb - wa), n_l);
             vs.init(cw, cwx, ge, K_s, n_ens + (uint32_t)(sb - sa), n_l);
-            // the target has no detection of this class from either detector: both variants are the same integral
-            const bool same = (wb == wa) && (sb == sa);
-            if (same) vs.dead = true;
-            if (same && !FULL) vw.dead = true;
+            if (same) vs.dead = true;             // FULL only: one integral serves both variants
             if (!(vw.dead && vs.dead)) {
                 OwnCursor ow, os;
                 ow.init(wq, wcb, wm, wa, wb, t);
