@@ -92,20 +92,21 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepArgs a) {
 }
 
 // ----------------------------------------------------------------------------
-// Everything after the host has laid out the classes, in ONE cooperative launch (five phases separated by grid
+// Everything after the host has laid out the classes, in ONE cooperative launch (three phases separated by grid
 // barriers; eight dependent launches of a few microseconds each before, whose enqueue cost exceeded their run time):
-//   1  padding slots of both streams: image M (never a member), no true positive
-//   2  position v of the combined (class, conf desc) order -> slot (weak) / insertion slot (strong)
-//      [wpre[v] = weak detections sorted before v]; labels into the class-major label stream (only the grouping by
-//      class matters — the label walk counts members per class — so a label takes the next free slot of its class)
-//   3  event counts per CTA range of chunks (event = slot holding a true positive);
+//   A  padding slots of both streams (image M = never a member, no true positive); position v of the combined
+//      (class, conf desc) order -> slot (weak) / insertion slot (strong) [wpre[v] = weak detections sorted before v];
+//      labels into the class-major label stream (only the grouping by class matters — the label walk counts members
+//      per class — so a label takes the next free slot of its class)
+//   B  event counts per CTA range of chunks (event = slot holding a true positive);
 //      own lists: the rows of one image and detector in (class, conf) order, i.e. ascending by their position in the
 //      global order — an image has a few hundred rows at most in practice, so one warp ranks them by counting instead
 //      of a dataset-wide regrouping sort — and the class-start table of the list: cs[img][c] = first entry with
-//      class >= c, c in [0, C]
-//   4  evbase = events in front of every chunk (exclusive scan), their total; per-batch query list: position v of the
-//      batch-major order IS the entry, ascending by slot with weak and strong rows interleaved
-//   5  each segment's first event; bqoff[b][s] = first query of batch b with slot >= first slot of segment s
+//      class >= c, c in [0, C];
+//      bqoff[b][s] = first query of batch b with slot >= first slot of segment s (searched through the batch-major
+//      order and the slots of phase A)
+//   C  evbase = events in front of every chunk (exclusive scan), their total, each segment's first event; per-batch
+//      query list: position v of the batch-major order IS the entry, ascending by slot, weak and strong interleaved
 // Arrays written in one phase and read in a later one are read with __ldcg (L2), never through the read-only path.
 // ----------------------------------------------------------------------------
 struct PostArgs {
@@ -113,7 +114,7 @@ struct PostArgs {
     int64_t n, M, C, G, P, PL, nchunks, S, nbatch, ev_per;
     const uint32_t *order, *wpre, *img_all, *ord_bat, *img_l;
     const int32_t *l_cls, *seg_chunk0;
-    const uint32_t *cls_off, *pad_off, *lpad_off;
+    const uint32_t *cls_off, *pad_off, *lcls_off, *lpad_off;
     const int64_t *w_off, *s_off;
     uint32_t *lcursor;
     uint32_t *slot_img, *lab_slot_img;
@@ -138,15 +139,17 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
     const int64_t gwarp = gtid >> 5, nwarps = gsize >> 5;
     unsigned epoch = 0;
 
-    // ---- 1
-    for (int64_t k = gtid; k < a.P; k += gsize) {
-        a.slot_img[k] = (uint32_t)a.M;
-        a.slot_tp[k] = 0;
+    // ---- A
+    for (int64_t k = gtid; k < a.C * 64; k += gsize) {           // at most 32 padding slots per class and stream
+        const int64_t c = k >> 6, i = k & 63;
+        const uint32_t slot = a.pad_off[c] + (a.cls_off[c + 1] - a.cls_off[c]) + (uint32_t)i;
+        if (slot < a.pad_off[c + 1]) {
+            a.slot_img[slot] = (uint32_t)a.M;
+            a.slot_tp[slot] = 0;
+        }
+        const uint32_t lslot = a.lpad_off[c] + (a.lcls_off[c + 1] - a.lcls_off[c]) + (uint32_t)i;
+        if (lslot < a.lpad_off[c + 1]) a.lab_slot_img[lslot] = (uint32_t)a.M;
     }
-    for (int64_t k = gtid; k < a.PL; k += gsize) a.lab_slot_img[k] = (uint32_t)a.M;
-    grid_sync(a.bar, epoch);
-
-    // ---- 2
     for (int64_t v = gtid; v < a.n; v += gsize) {
         const uint32_t u = a.order[v];
         const int c = a.d.cls(u);
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
     }
     grid_sync(a.bar, epoch);
 
-    // ---- 3: events of this CTA's chunk range, split over its warps
+    // ---- B: events of this CTA's chunk range, split over its warps
     const int64_t c0 = (int64_t)blockIdx.x * a.ev_per, c1 = c0 + a.ev_per < a.nchunks ? c0 + a.ev_per : a.nchunks;
     const int64_t cw = (a.ev_per + kPostWarps - 1) / kPostWarps;
     const int64_t w0 = c0 + warp * cw, w1 = w0 + cw < c1 ? w0 + cw : c1;
@@ -218,9 +221,24 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
             row[c] = (uint16_t)lo;
         }
     }
+    for (int64_t k = gtid; k < a.nbatch * (a.S + 1); k += gsize) {
+        const int64_t b = k / (a.S + 1), s = k % (a.S + 1);
+        const int64_t i0 = b * 32 < a.M ? b * 32 : a.M, i1 = (b + 1) * 32 < a.M ? (b + 1) * 32 : a.M;
+        int64_t lo = a.w_off[i0] + a.s_off[i0], hi = a.w_off[i1] + a.s_off[i1];
+        if (s < a.S) {
+            const uint32_t slot0 = (uint32_t)a.seg_chunk0[s] * 32u;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldcg(a.q_of_det + a.ord_bat[mid]) < slot0) lo = mid + 1; else hi = mid;
+            }
+        } else {
+            lo = hi;
+        }
+        a.bqoff[k] = (uint32_t)lo;
+    }
     grid_sync(a.bar, epoch);
 
-    // ---- 4
+    // ---- C
     {
         uint32_t before = 0, all = 0;
         for (int b = threadIdx.x; b < (int)gridDim.x; b += kPostThreads) {
@@ -235,7 +253,15 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
         uint32_t run = carry + warp_base;
         for (int64_t ch = w0; ch < w1; ++ch) {
             const unsigned b = __ballot_sync(kFull, __ldcg(a.slot_tp + ch * 32 + lane) != 0);
-            if (lane == 0) a.evbase[ch] = run;
+            if (lane == 0) {
+                a.evbase[ch] = run;
+                int64_t lo = 0, hi = a.S;                  // is this chunk the first of a segment?
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (a.seg_chunk0[mid] < ch) lo = mid + 1; else hi = mid;
+                }
+                if (lo < a.S && a.seg_chunk0[lo] == ch) a.seg_ev0[lo] = run;
+            }
             run += __popc(b);
         }
     }
@@ -243,25 +269,6 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
         const uint32_t u = a.ord_bat[v];
         a.bq[v] = make_uint2(__ldcg(a.q_of_det + u) | (u >= a.d.Dw ? 0x80000000u : 0u),
                              ((a.img_all[u] & 31u) << 27) | __ldcg(a.ownpos + u));
-    }
-    grid_sync(a.bar, epoch);
-
-    // ---- 5
-    for (int64_t s = gtid; s < a.S; s += gsize) a.seg_ev0[s] = __ldcg(a.evbase + a.seg_chunk0[s]);
-    for (int64_t k = gtid; k < a.nbatch * (a.S + 1); k += gsize) {
-        const int64_t b = k / (a.S + 1), s = k % (a.S + 1);
-        const int64_t i0 = b * 32 < a.M ? b * 32 : a.M, i1 = (b + 1) * 32 < a.M ? (b + 1) * 32 : a.M;
-        int64_t lo = a.w_off[i0] + a.s_off[i0], hi = a.w_off[i1] + a.s_off[i1];
-        if (s < a.S) {
-            const uint32_t slot0 = (uint32_t)a.seg_chunk0[s] * 32u;
-            while (lo < hi) {
-                const int64_t mid = (lo + hi) >> 1;
-                if ((__ldcg(&a.bq[mid].x) & 0x7fffffffu) < slot0) lo = mid + 1; else hi = mid;
-            }
-        } else {
-            lo = hi;
-        }
-        a.bqoff[k] = (uint32_t)lo;
     }
 }
 
@@ -524,9 +531,10 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     }
     for (int64_t c = 0; c < C; ++c) cls_order[c] = (int32_t)c;
     std::stable_sort(cls_order.begin(), cls_order.end(), [&](int32_t a, int32_t b) { return h_hist[a] > h_hist[b]; });
-    uint32_t *d_cls_off, *d_pad_off, *d_lpad_off, *d_tables;
+    uint32_t *d_cls_off, *d_pad_off, *d_lcls_off, *d_lpad_off, *d_tables;
     tab.add(&d_cls_off, LD.cls_off);
     tab.add(&d_pad_off, LD.pad_off);
+    tab.add(&d_lcls_off, LL.cls_off);
     tab.add(&d_lpad_off, LL.pad_off);
     tab.add(&ix->seg_chunk0, LD.seg_chunk0);
     tab.add(&ix->seg_nch, LD.seg_nch);
@@ -559,7 +567,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         pa.nbatch = ix->nbatch;
         pa.order = order; pa.wpre = wpre; pa.img_all = img_all; pa.ord_bat = ord_bat; pa.img_l = img_l;
         pa.l_cls = l_cls; pa.seg_chunk0 = ix->seg_chunk0;
-        pa.cls_off = d_cls_off; pa.pad_off = d_pad_off; pa.lpad_off = d_lpad_off;
+        pa.cls_off = d_cls_off; pa.pad_off = d_pad_off; pa.lcls_off = d_lcls_off; pa.lpad_off = d_lpad_off;
         pa.w_off = ix->w_off; pa.s_off = ix->s_off;
         pa.lcursor = lcursor;
         pa.slot_img = ix->slot_img; pa.lab_slot_img = ix->lab_slot_img; pa.slot_tp = ix->slot_tp;
@@ -570,6 +578,14 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         pa.bar = (unsigned *)scratch;
         pa.table = (uint32_t *)(scratch + 256);
         pa.total_out = d_total;
+        // three CTAs per SM: more only make the grid barriers dearer (measured, profiles/)
+        {
+            int dev = 0, sms = 0;
+            ORIE_CUDA(cudaGetDevice(&dev));
+            ORIE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            post_blocks = std::min(post_blocks, 3 * sms);
+        }
+        if (const char *cap = getenv("ORIE_POST_BLOCKS")) post_blocks = std::max(1, std::min(post_blocks, atoi(cap)));   // developer knob
         const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(post_blocks, ceil_div(std::max(n, ix->P), kPostThreads)));
         pa.ev_per = ceil_div(std::max<int64_t>(ix->nchunks, 1), blocks);
         ORIE_CUDA(cudaMemsetAsync(pa.bar, 0, 4, st));
