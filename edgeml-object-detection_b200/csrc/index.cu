@@ -128,7 +128,7 @@ struct PostArgs {
 };
 constexpr int kPostThreads = 256;
 constexpr int kPostWarps = kPostThreads / 32;
-constexpr int kRankStage = 256;          // rows of an image staged in shared memory for the ranking
+constexpr int kRankStage = 512;          // rows of an image staged in shared memory for the ranking
 
 __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
     __shared__ uint32_t ws[kPostWarps];
@@ -190,24 +190,33 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
         uint16_t *own_m = strong ? a.own_s_m : a.own_w_m, *own_c = strong ? a.own_s_c : a.own_w_c;
         const uint16_t *tp = strong ? a.d.s_tp : a.d.w_tp;
         const int32_t *cls = strong ? a.d.s_cls : a.d.w_cls;
-        const bool fits = n <= kRankStage;
+        const bool fits = n <= kRankStage;      // the usual case: the image's positions are staged once
         __syncwarp();
         if (fits)
             for (int k = lane; k < n; k += 32) staged[warp][k] = __ldcg(pos + k);
         __syncwarp();
-        for (int r = lane; r < n; r += 32) {
-            const uint32_t me = fits ? staged[warp][r] : __ldcg(pos + r);
+        for (int rb = 0; rb < n; rb += 32) {     // uniform trip count: the staging below is warp-wide
+            const int r = rb + lane;
+            const uint32_t me = r < n ? (fits ? staged[warp][r] : __ldcg(pos + r)) : 0u;
             int rank = 0;
             if (fits) {
                 for (int k = 0; k < n; ++k) rank += staged[warp][k] < me;
             } else {
-                for (int k = 0; k < n; ++k) rank += __ldcg(pos + k) < me;
+                for (int t0 = 0; t0 < n; t0 += kRankStage) {          // larger images: tile by tile through the stage
+                    const int cnt = n - t0 < kRankStage ? n - t0 : kRankStage;
+                    __syncwarp();
+                    for (int k = lane; k < cnt; k += 32) staged[warp][k] = __ldcg(pos + t0 + k);
+                    __syncwarp();
+                    for (int k = 0; k < cnt; ++k) rank += staged[warp][k] < me;
+                }
             }
-            const int64_t at = r0 + rank;
-            own_q[at] = __ldcg(a.q_of_det + u0 + r);
-            own_m[at] = tp[r0 + r];
-            own_c[at] = (uint16_t)cls[r0 + r];
-            a.ownpos[u0 + r] = (uint32_t)at;
+            if (r < n) {
+                const int64_t at = r0 + rank;
+                own_q[at] = __ldcg(a.q_of_det + u0 + r);
+                own_m[at] = tp[r0 + r];
+                own_c[at] = (uint16_t)cls[r0 + r];
+                a.ownpos[u0 + r] = (uint32_t)at;
+            }
         }
         __syncwarp();                      // the list of this image is complete (written by this warp)
         const uint16_t *list = own_c + r0;

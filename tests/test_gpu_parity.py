@@ -206,3 +206,20 @@ def test_confidence_ties_and_many_classes_follow_the_tie_rule():
     want = np.array([_orie_with_the_engine_tie_rule(i, wd, sd, lc, em[i]) for i in range(M)])
     assert np.abs(got - want).max() < 1e-9
     eng.close()
+
+
+def test_images_with_more_rows_than_the_ranking_stage():
+    """Own lists are ranked per image in a 512-row shared-memory stage; images with more rows go through it tile by
+    tile."""
+    from orie_b200 import data, synth
+    from orie_b200.synth import DetectorShape
+    M, N = 40, 15
+    ds = synth.generate(M, 12, 6.0, 0.0, DetectorShape(.6, .08, 700, 1500), DetectorShape(.8, .04, 600, 1200), 91)
+    pk = data.pack(ds.labels, ds.weak, ds.strong)
+    assert np.diff(pk.w_off).max() > 512 and np.diff(pk.s_off).max() > 512
+    eng = _engine(pk, O.IOU_05_095)
+    em = O.ensemble_matrix(M, N, 2)
+    got = eng.orie(N, ens_matrix=em)
+    wd, sd, lc = oracle_cache(pk, O.IOU_05_095)
+    assert np.abs(got - O.orie_all(wd, sd, lc, em)).max() < 1e-9
+    eng.close()
