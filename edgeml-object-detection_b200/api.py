@@ -79,7 +79,7 @@ def set_data(weak, strong, label, iouv=IOU_05, device=None):
 
 
 def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", num_ensemble=1000, iouv=IOU_05,
-                              seed=None, ensembles="device", device=None, verbose=True):
+                              seed=None, ensembles="device", device=None, verbose=True, shard="auto"):
     """What ``reward.py:main`` does between parsing and saving.
 
     Returns (reward ndarray, seconds, info).  ``seconds`` covers what the
@@ -127,7 +127,7 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
     # Multi-GPU: every rank keeps all images and its share of the classes (AP sums are additive over classes), runs
     # the whole pipeline for all targets and one all-reduce of 3 doubles per target combines the ranks.
     from .engine import HostPacked
-    by_class = dist is not None and method == "orie" and pick_shard(M) == "classes"
+    by_class = dist is not None and method == "orie" and pick_shard(M, shard) == "classes"
     by_target = dist is not None and method == "orie" and not by_class
     eng = Engine(HostPacked(class_shard(pk, rank, world) if by_class else pk), iouv=iouv, device=device)
     torch.cuda.synchronize()

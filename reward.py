@@ -38,6 +38,9 @@ def getargs(argv=None):
     args.add_argument('--ensembles', type=str, default="device", choices=['device', 'numpy'],
                       help="'device': counter-based draw on the GPU; 'numpy': regenerate the reference's "
                            "np.random.permutation draw on the host with seed+image index (parity runs).")
+    args.add_argument('--shard', type=str, default="auto", choices=['auto', 'classes', 'targets'],
+                      help="Multi-GPU decomposition under torchrun: 'classes' (one all-reduce of per-target AP sums), "
+                           "'targets' (one all-gather of reward slices), 'auto' = by dataset size.")
     return args.parse_args(argv)
 
 
@@ -46,7 +49,7 @@ def main(opts):
     from orie_b200 import api
     reward, seconds, info = api.compute_rewards_from_dirs(
         opts.weak_dir, opts.strong_dir, opts.label_dir, method=opts.method, num_ensemble=opts.num_ensemble,
-        iouv=opts.iou_thresholds, seed=opts.seed, ensembles=opts.ensembles)
+        iouv=opts.iou_thresholds, seed=opts.seed, ensembles=opts.ensembles, shard=opts.shard)
     if int(os.environ.get("RANK", "0")) == 0:
         print(f"Program takes {seconds:.1f} seconds ({seconds / 60:.1f}m/{seconds / 3600:.2f}h).")
         path = api.save_rewards(opts.save_dir, opts.method, opts.num_ensemble, reward, seconds)
