@@ -110,3 +110,30 @@ def test_native_reader_matches_the_live_reference_loader(tmp_path):
             assert np.array_equal(rec[1], data.xywh_to_xyxy(mine[:, 1:5]))
             if conf:
                 assert np.array_equal(rec[2], mine[:, 5])
+
+
+def test_native_reader_random_number_spellings(tmp_path):
+    """Every spelling a detector or a conversion script might emit (%g, %e, %f with few or many digits, repr, integers,
+    leading '+', trailing '.', huge and tiny magnitudes) parses to the same float64 bits as Python's float()."""
+    rng = np.random.default_rng(12)
+    d = tmp_path / "dets"
+    d.mkdir()
+    fmts = ["%r", "%g", "%.17g", "%e", "%.3e", "%f", "%.10f", "%.1f", "%+g", "%d."]
+    names = []
+    for i in range(40):
+        rows = []
+        for _ in range(int(rng.integers(0, 30))):
+            vals = np.concatenate([[float(rng.integers(0, 80))], rng.random(4), [rng.random() * 10.0 ** rng.integers(-12, 3)]])
+            toks = []
+            for v in vals:
+                f = fmts[int(rng.integers(len(fmts)))]
+                toks.append(repr(float(v)) if f == "%r" else (f % int(v) if f == "%d." else f % v))
+            rows.append(" ".join(toks))
+        name = f"img{i:03d}"
+        names.append(name)
+        (d / f"{name}.txt").write_text("\n".join(rows) + ("\n" if rows and rng.random() < 0.7 else ""))
+    py = data.read_rows(str(d), names, True, native=False)
+    nat = data.read_rows(str(d), names, True, native=True)
+    assert same_rows(nat, py) and len(py.rows) > 100
+    off, rows, fb = _io.read_rows(str(d), names, True)
+    assert len(fb) == 0                                         # all of it on the fast path
