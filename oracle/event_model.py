@@ -238,8 +238,9 @@ def ap_reverse(ix, c, t, tot, events, own, n_l):
 
 def delta_reverse(ix, c, t, tot, events, own_w, own_s, n_l):
     """AP_strong - AP_weak of class c at threshold bit t, the way ap_kernel<false> computes it: both variants are
-    swept together and the sweep stops once they can no longer differ (all own detections behind, equal envelope,
-    equal remaining-TP count and grid pointer) — every later term is identical in both and cancels."""
+    swept together and the sweep stops once they can no longer differ (all own detections behind and either no true
+    positive left in front, or equal envelopes at an equal remaining-TP count and grid pointer) — every later term is
+    identical in both and cancels."""
     if len(own_w[0]) == 0 and len(own_s[0]) == 0:
         return 0.0, 0
     s0, s1 = ix.cls_seg0[c], ix.cls_seg0[c + 1]
@@ -260,8 +261,20 @@ def delta_reverse(ix, c, t, tot, events, own_w, own_s, n_l):
             cur[v] -= 1
 
     def converged():
+        """ap_kernel's two exits once every own detection lies behind: (1) no true positive is left in front of either
+        variant, nothing can change any more; (2) both alive — they then share the remaining-TP count and the grid
+        pointer (asserted here: it is what lets the kernel's tail loop keep ONE copy of that state and compute one
+        ratio per event for both variants) — and the envelopes have met."""
         a, b = var
-        return cur[0] < 0 and cur[1] < 0 and a.E == b.E and a.k == b.k and a.g == b.g
+        if cur[0] >= 0 or cur[1] >= 0:
+            return False
+        ka, kb = (0 if a.dead else a.k), (0 if b.dead else b.k)
+        if ka == 0 and kb == 0:
+            return True
+        if not a.dead and not b.dead:
+            assert a.k == b.k and a.g == b.g, (a.k, b.k, a.g, b.g)
+            return a.E == b.E
+        return False
 
     if not (var[0].dead and var[1].dead):
         rem, done = n_ens, False
