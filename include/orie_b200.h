@@ -110,7 +110,7 @@ int orie_index_build(int64_t M, int64_t C, int T,
                      const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                      const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
                      const int64_t *l_off, const int32_t *l_cls,
-                     int seg_chunks /* 0 = auto */, orie_event_t tp_ready /* nullable */,
+                     int seg_chunks /* 0 = auto; at most 2047 (clamped) */, orie_event_t tp_ready /* nullable */,
                      orie_stream_t stream, orie_index_t **out);
 void orie_index_destroy(orie_index_t *idx);
 int orie_index_info(const orie_index_t *idx, orie_index_info_t *info);
