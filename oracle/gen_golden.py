@@ -28,6 +28,8 @@ CASES = [
     # name, config, M, seed, generator kwargs, [(T, N, base_seed)]
     ("coco48", "smoke500", 48, 31, dict(empty_det_frac=0.05), [(1, 12, 500), (10, 12, 500), (10, 0, 7), (1, 1000, 9)]),
     ("voc40", "voc4952", 40, 32, dict(empty_det_frac=0.0, zipf=1.0), [(10, 20, 11), (1, 39, 12)]),
+    # the scale-sweep shape: exactly 300 rows per image and detector
+    ("dense24", "sweep50k", 24, 33, dict(), [(10, 8, 21), (10, 23, 22), (1, 0, 5)]),
 ]
 
 
@@ -36,10 +38,12 @@ def flat(cache, T):
     return np.concatenate(tp, axis=0) if tp else np.zeros((0, T), dtype=bool)
 
 
-def main():
+def main(only=None):
     assert R.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     for name, config, M, seed, kw, runs in CASES:
+        if only and name not in only:
+            continue
         ds = synth.make(config, num_images=M, seed=seed, **kw)
         # make the edge cases explicit: an image without labels but with detections, one with nothing at all
         out = dict(names=np.array(ds.names), num_classes=ds.num_classes,
@@ -91,5 +95,8 @@ def main_testmap():
 
 
 if __name__ == "__main__":
-    main()
-    main_testmap()
+    if len(sys.argv) > 1:           # python oracle/gen_golden.py dense24  -> only the named fixtures
+        main(only=sys.argv[1:])
+    else:
+        main()
+        main_testmap()
