@@ -22,9 +22,8 @@ def load():
         try:
             _build.build_io()
         except Exception as e:  # noqa: BLE001
-            if not os.path.exists(_build.IO_LIB):
-                raise RuntimeError(f"liborie_io.so is missing and could not be built ({e}); "
-                                   "pass native=False to use the Python reader") from e
+            raise RuntimeError(f"liborie_io.so is missing or older than its sources and could not be rebuilt ({e}); "
+                               "pass native=False to use the Python reader") from e
     lib = C.CDLL(_build.IO_LIB)
     vp, i64 = C.c_void_p, C.c_int64
     lib.orie_io_last_error.restype = C.c_char_p

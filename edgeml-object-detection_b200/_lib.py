@@ -50,13 +50,14 @@ def load():
         return _LIB
     path = _build.LIB
     if not os.path.exists(path) or (_build.stale() and os.path.exists(_build.nvcc_or_none() or "")):
+        # sources newer than the library (or no library): rebuild under the build lock.  A failed rebuild is an
+        # error even if an older library is still lying around — never run a binary that is not the sources'.
         try:
             _build.build()
         except Exception as e:  # noqa: BLE001
-            if not os.path.exists(path):
-                raise RuntimeError(
-                    "liborie_b200.so is missing and could not be built; the engine has no CPU fallback. "
-                    f"Build it with `python -c 'import __graft_entry__ as g; g.build()'` ({e})") from e
+            raise RuntimeError(
+                "liborie_b200.so is missing or older than its sources and could not be rebuilt; the engine has no "
+                f"CPU fallback. Build it with `python -c 'import __graft_entry__ as g; g.build()'` ({e})") from e
     lib = C.CDLL(path)
     vp, i64, i32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_uint64
     lib.orie_last_error.restype = C.c_char_p

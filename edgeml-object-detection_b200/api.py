@@ -44,7 +44,7 @@ def ensemble_matrix_numpy(num_images: int, num_ensemble: int, base_seed: int, t0
         others = np.arange(num_images - 1)
         if i < num_images - 1:
             others[i:] += 1
-        out[r] = np.random.RandomState(base_seed + i).permutation(others)[:n]
+        out[r] = np.random.RandomState((base_seed + i) % 2**32).permutation(others)[:n]
     return out
 
 
@@ -82,10 +82,12 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
                               seed=None, ensembles="device", device=None, verbose=True, shard="auto"):
     """What ``reward.py:main`` does between parsing and saving.
 
-    Returns (reward ndarray, seconds, info).  ``seconds`` covers what the
-    reference's own timer covers (the reward phase, reward.py:76-88) — here the
-    index build, the ensemble draw and the reward kernels; loading and TP
-    matching are reported separately in ``info`` like upstream's ``set_data``.
+    Returns (reward ndarray, seconds, info).  ``seconds`` (saved as ``time``) covers AT LEAST what the
+    reference's own timer covers (the reward phase, reward.py:76-88): the dataset sort / index build that
+    replaces upstream's per-target argsort, the ensemble draw and the reward kernels — and, because the engine
+    overlaps it with the sort, also the upload and TP matching that upstream's timer leaves out (``set_data``).
+    File loading is reported separately in ``info`` (``load_s``); ``match_index_s`` is the part of ``seconds``
+    spent before the first reward kernel.
     Under torchrun (WORLD_SIZE > 1) the classes are sharded over the ranks and the
     per-target AP sums are combined with one NCCL all-reduce; datasets beyond ~28 k images
     shard the targets instead (one all-gather of reward slices), see ``engine.pick_shard``."""
@@ -129,11 +131,12 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
     from .engine import HostPacked
     by_class = dist is not None and method == "orie" and pick_shard(M, shard) == "classes"
     by_target = dist is not None and method == "orie" and not by_class
-    eng = Engine(HostPacked(class_shard(pk, rank, world) if by_class else pk), iouv=iouv, device=device)
+    eng = Engine(HostPacked(class_shard(pk, rank, world) if by_class else pk), iouv=iouv, device=device,
+                 index=method != "dcsb")
     torch.cuda.synchronize()
     t_match = time.perf_counter() - t
     try:
-        start = time.perf_counter()
+        start = t            # the timer includes the index build (upstream sorts inside its timer) and the matching
         if method == "dcsb":
             reward = eng.dcsb().astype(int)
         else:

@@ -2,6 +2,8 @@
 file reader liborie_io.so with g++."""
 from __future__ import annotations
 
+import contextlib
+import fcntl
 import os
 import shutil
 import subprocess
@@ -42,16 +44,42 @@ def stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+@contextlib.contextmanager
+def _build_lock():
+    """One builder at a time per checkout (every rank of a torchrun job imports this module at once)."""
+    with open(os.path.join(HERE, ".build.lock"), "w") as f:
+        fcntl.flock(f, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(f, fcntl.LOCK_UN)
+
+
+def _compile(cmd, out) -> str:
+    """Run ``cmd + ['-o', tmp]`` and move the result into place atomically, so a process that is loading
+    ``out`` never sees a half-written library."""
+    tmp = f"{out}.{os.getpid()}.tmp"
+    try:
+        res = subprocess.run(cmd + ["-o", tmp], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("build failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        os.replace(tmp, out)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+    return res.stdout + res.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    with _build_lock():
+        if not force and not stale():      # another process built it while this one waited for the lock
+            return LIB
+        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, f) for f in SOURCES]
+        log = _compile(cmd, LIB)
     if verbose:
-        print(res.stdout + res.stderr)
+        print(log)
     return LIB
 
 
@@ -69,11 +97,11 @@ def build_io(force: bool = False) -> str:
     gxx = shutil.which("g++") or shutil.which("c++")
     if gxx is None:
         raise RuntimeError("g++ not found; liborie_io.so cannot be built")
-    cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-pthread"] + \
-          [os.path.join(CSRC, f) for f in IO_SOURCES] + ["-o", IO_LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    with _build_lock():
+        if not force and not io_stale():
+            return IO_LIB
+        _compile([gxx, "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-pthread"] +
+                 [os.path.join(CSRC, f) for f in IO_SOURCES], IO_LIB)
     return IO_LIB
 
 

@@ -10,6 +10,7 @@
 // detection's place among the weak ones is the number of weak detections sorted
 // before it.  See DESIGN.md §3 for the layout.
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "coop.cuh"
@@ -287,8 +288,36 @@ static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
     return b;
 }
 
-// Stream-ordered arena: the sizes are collected first, then ONE cudaMallocAsync backs all of them (the
-// device's default pool keeps its memory between builds: the release threshold is raised once).
+// The index's memory comes from a stream-ordered pool that is PRIVATE to this library (one per device, created on
+// first use, never trimmed so that rebuilding an index does not go back to the driver).  The device's default pool
+// — which the host application may be using — is never touched.
+static int engine_pool(cudaMemPool_t *out) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    ORIE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) {
+        set_error("orie_index_build: device ordinal %d not supported", dev);
+        return ORIE_ELIMIT;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool;
+        ORIE_CUDA(cudaMemPoolCreate(&pool, &props));
+        uint64_t keep_all = UINT64_MAX;
+        ORIE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
+        pools[dev] = pool;
+    }
+    *out = pools[dev];
+    return ORIE_OK;
+}
+
+// Stream-ordered arena: the sizes are collected first, then ONE allocation from the library's pool backs all of them.
 struct Arena {
     struct Item {
         void **p;
@@ -303,7 +332,9 @@ struct Arena {
         size_t total = 0;
         for (auto &it : items) total += it.bytes;
         void *q = nullptr;
-        ORIE_CUDA(cudaMallocAsync(&q, std::max<size_t>(total, 256), st));
+        cudaMemPool_t pool;
+        ORIE_TRY(engine_pool(&pool));
+        ORIE_CUDA(cudaMallocFromPoolAsync(&q, std::max<size_t>(total, 256), pool, st));
         size_t at = 0;
         for (auto &it : items) {
             *it.p = (char *)q + at;
@@ -402,14 +433,6 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     Tables tab;
     uint32_t h_total = 0;
     Builder B{ix, st};
-    {
-        int dev = 0;
-        cudaMemPool_t pool;
-        uint64_t keep_all = UINT64_MAX;
-        ORIE_CUDA(cudaGetDevice(&dev));
-        ORIE_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        ORIE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
-    }
     // ---- sizes: given by the caller; off[M] of each block is cross-checked on the device (status bit 2)
     const int64_t Dw = ix->Dw, Ds = ix->Ds, G = ix->G;
     if (Dw < 0 || Ds < 0 || G < 0 || Dw >= ((int64_t)1 << 27) || Ds >= ((int64_t)1 << 27) || G >= ((int64_t)1 << 31)) {

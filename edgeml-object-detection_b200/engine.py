@@ -141,10 +141,11 @@ class DevicePacked:
 
 
 class Engine:
-    def __init__(self, packed, iouv=IOU_05, device=None, seg_chunks: int = 0, stream=None):
+    def __init__(self, packed, iouv=IOU_05, device=None, seg_chunks: int = 0, stream=None, index: bool = True):
         """``packed``: ``Packed`` (host numpy), ``HostPacked`` (pinned) or
         ``DevicePacked`` (already in HBM).  Uploads if needed, then runs TP
-        matching for both detectors and builds the dataset index."""
+        matching for both detectors and builds the dataset index (``index=False``: matching only — all
+        that ``tp_flags`` and ``dcsb`` need, what upstream's ``set_data`` does)."""
         if not torch.cuda.is_available():
             raise RuntimeError("orie_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -157,6 +158,8 @@ class Engine:
         self._handle = C.c_void_p(0)
         self._ws = None
         self._status = None
+        self._want_index = bool(index)
+        self.info = {}
         with torch.cuda.device(self.device):
             self.stream = stream or torch.cuda.current_stream()
             with torch.cuda.stream(self.stream):
@@ -240,6 +243,8 @@ class Engine:
         self.s_tp, self.s_match, self.s_biou = run(self.s_box, self.s_cls, self.s_off, self.Ds)
 
     def _build_index(self, seg_chunks, tp_ready):
+        if not self._want_index:
+            return
         h = C.c_void_p(0)
         ev = C.c_void_p(tp_ready.cuda_event) if tp_ready is not None else C.c_void_p(0)
         _lib.check(self.lib.orie_index_build(

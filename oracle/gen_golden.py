@@ -30,7 +30,38 @@ CASES = [
     ("voc40", "voc4952", 40, 32, dict(empty_det_frac=0.0, zipf=1.0), [(10, 20, 11), (1, 39, 12)]),
     # the scale-sweep shape: exactly 300 rows per image and detector
     ("dense24", "sweep50k", 24, 33, dict(), [(10, 8, 21), (10, 23, 22), (1, 0, 5)]),
+    # duplicate ground-truth boxes (exact IoU ties between same-class labels): upstream's argsort of the candidate
+    # pairs (lib/metrics.py:59) is deterministic below 16 elements (insertion sort + reversal -> the HIGHEST label
+    # row wins a tie), which is the rule the engine implements; images are kept small so every image stays below 16
+    ("ties24", None, 24, 34, dict(), [(10, 6, 41), (1, 23, 42), (10, 0, 43)]),
 ]
+
+
+def tied_dataset(M, seed):
+    """Small images whose label files repeat rows verbatim (same class, same box), so that a detection has the same
+    IoU with two labels.  Fewer than 16 candidate (label, detection) pairs per image and threshold (asserted)."""
+    from orie_b200.synth import DetectorShape, Rows
+    from oracle import orie_oracle as O
+    ds = synth.generate(M, 4, 2.0, 0.0, DetectorShape(.9, .05, 4, 6), DetectorShape(.95, .03, 4, 6), seed)
+    rng = np.random.default_rng(seed)
+    rows, off = [], [0]
+    for i in range(M):
+        lab = ds.labels.image(i)
+        if len(lab) and i % 4 != 3:                     # three images in four get 1-2 duplicated rows
+            k = int(rng.integers(1, 3))
+            dup = lab[rng.integers(0, len(lab), size=k)]
+            lab = np.concatenate([lab, dup], axis=0)[rng.permutation(len(lab) + k)]
+        rows.append(lab)
+        off.append(off[-1] + len(lab))
+    ds.labels = Rows(np.array(off, dtype=np.int64), np.ascontiguousarray(np.concatenate(rows, axis=0)))
+    for det in (ds.weak, ds.strong):                    # the determinism precondition
+        for i in range(M):
+            d, l = det.image(i), ds.labels.image(i)
+            if len(d) and len(l):
+                iou = O.pairwise_iou(O.xywh_to_xyxy(l[:, 1:5]), O.xywh_to_xyxy(d[:, 1:5]))
+                cand = (iou >= 0.5) & (l[:, :1] == d[None, :, 0])
+                assert cand.sum() < 16, (i, int(cand.sum()))
+    return ds
 
 
 def flat(cache, T):
@@ -44,7 +75,7 @@ def main(only=None):
     for name, config, M, seed, kw, runs in CASES:
         if only and name not in only:
             continue
-        ds = synth.make(config, num_images=M, seed=seed, **kw)
+        ds = tied_dataset(M, seed) if config is None else synth.make(config, num_images=M, seed=seed, **kw)
         # make the edge cases explicit: an image without labels but with detections, one with nothing at all
         out = dict(names=np.array(ds.names), num_classes=ds.num_classes,
                    l_off=ds.labels.off, l_rows=ds.labels.rows, w_off=ds.weak.off, w_rows=ds.weak.rows,

@@ -219,7 +219,7 @@ def ensemble_indices(num_img: int, img_idx: int, num_ensemble: int, seed: int) -
     others = np.arange(num_img - 1)
     if img_idx < num_img - 1:
         others[img_idx:] += 1
-    state = np.random.RandomState(seed)
+    state = np.random.RandomState(seed % 2**32)
     return state.permutation(others)[:n]
 
 

@@ -66,3 +66,29 @@ def test_box_correct_random_cases():
         want = R.ref_box_correct(np.column_stack([det, conf, dc]), np.column_stack([lc, lab]), iouv)
         got, _, _ = O.match_detections(det, dc, lab, lc, iouv)
         assert np.array_equal(got, want)
+
+
+def test_box_correct_with_duplicate_labels_iou_ties():
+    """Exact IoU ties (a label row repeated verbatim): upstream's argsort (lib/metrics.py:59) is deterministic below 16
+    candidate pairs, and the oracle's rule (ties -> highest label row, the engine's match.cu rule) reproduces its flags."""
+    rng = np.random.default_rng(7)
+    iouv = O.IOU_05_095
+    checked = 0
+    for _ in range(400):
+        n, m = int(rng.integers(1, 5)), int(rng.integers(1, 3))
+        det = rng.uniform(0, 1, (n, 2)); det = np.concatenate([det, det + rng.uniform(0.05, 0.4, (n, 2))], axis=1)
+        lab = det[rng.integers(0, n, m)] + rng.normal(0, 0.02, (m, 4))
+        lc = rng.integers(0, 2, m)
+        k = int(rng.integers(1, 3))                       # repeat 1-2 label rows verbatim, shuffled into the file
+        pick = rng.integers(0, m, k)
+        perm = rng.permutation(m + k)
+        lab, lc = np.concatenate([lab, lab[pick]])[perm], np.concatenate([lc, lc[pick]])[perm]
+        dc = rng.integers(0, 2, n)
+        conf = rng.random(n)
+        if ((O.pairwise_iou(lab, det) >= 0.5) & (lc[:, None] == dc[None, :])).sum() >= 16:
+            continue
+        want = R.ref_box_correct(np.column_stack([det, conf, dc]), np.column_stack([lc, lab]), iouv)
+        got, _, _ = O.match_detections(det, dc, lab, lc, iouv)
+        assert np.array_equal(got, want)
+        checked += 1
+    assert checked > 300
