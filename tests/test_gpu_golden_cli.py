@@ -171,7 +171,7 @@ def test_full_size_coco_shape_properties():
     assert (member.sum(1) == N).all()
     sys.path.insert(0, ROOT)
     import bench
-    wd, sd, lc = bench.cpu_cache_from_packed(pk, O.IOU_05_095, wtp, stp)
+    wd, sd, lc = bench.cpu_cache_from_flags(pk, O.IOU_05_095, wtp, stp)
     for r, i in enumerate(targets):
         want = O.orie_one(i, wd, sd, lc, np.nonzero(member[r])[0])[0]
         assert abs(r1[i] - (0 if np.isnan(want) else want)) < 1e-6
