@@ -429,9 +429,9 @@ def run_b200(args):
                 phase_ms["reward_ms"].append(e1.elapsed_time(e2))
             eng.close()
             return e0.elapsed_time(e2), {}
-        wave = eng.wave_size(nt, args.workspace_gb << 30) if nt > 0 else 0
-        ws = eng._workspace(eng.workspace_bytes(wave))
-        bits = torch.empty((max(wave, 1), eng.info["ens_words"]), dtype=torch.int32, device=dev)
+        wave, ws_bytes = eng.plan_waves(nt, args.workspace_gb << 30)      # no synchronisation when the bound fits the budget
+        ws = eng._workspace(ws_bytes)
+        bits = torch.empty((max(wave, 1), eng.ens_words), dtype=torch.int32, device=dev)
         mine = torch.zeros(per, dtype=torch.float64, device=dev)
         sums = torch.zeros((M, 3), dtype=torch.float64, device=dev) if by_class else None
         ms = [0.0] * 4
@@ -466,7 +466,8 @@ def run_b200(args):
         elif record:
             phase_ms["match_index_ms"].append(e0.elapsed_time(e1))
             phase_ms["reward_ms"].append(e1.elapsed_time(e2))
-        info = eng.info
+        info = eng.info                      # after the timed region: the exact sizes (the build itself never synchronised)
+        eng.check_status()
         eng.close()
         return e0.elapsed_time(e2), info
 

@@ -15,9 +15,10 @@ _LIB = None
 c_i64p = C.c_void_p   # device pointers are passed as plain addresses
 SYMBOLS = [
     "orie_last_error", "orie_version", "orie_match", "orie_dcsb",
-    "orie_index_build", "orie_index_destroy", "orie_index_info",
+    "orie_index_build", "orie_index_destroy", "orie_index_info", "orie_index_status",
     "orie_ensemble_from_indices", "orie_ensemble_sample",
-    "orie_reward_workspace_bytes", "orie_reward", "orie_reward_sums", "orie_reward_profile", "orie_launch_count",
+    "orie_reward_workspace_bytes", "orie_reward_workspace_bound", "orie_reward", "orie_reward_sums", "orie_rewards_from_sums",
+    "orie_reward_profile", "orie_reward_depths", "orie_launch_count",
     "orie_rank_workspace_bytes", "orie_rank_normalize",
 ]
 
@@ -31,6 +32,11 @@ class IndexInfo(C.Structure):
         ("label_slots", C.c_int64), ("label_segments", C.c_int64),
         ("class_groups", C.c_int64), ("ens_words", C.c_int64), ("device_bytes", C.c_int64),
     ]
+
+
+class Tuning(C.Structure):
+    _fields_ = [("seg_chunks", C.c_int32), ("sort_max_blocks", C.c_int32), ("post_blocks", C.c_int32),
+                ("walk_gmem", C.c_int32), ("ap_mode", C.c_int32), ("reserved", C.c_int32), ("walk_waves", C.c_double)]
 
 
 class OrieError(RuntimeError):
@@ -68,7 +74,16 @@ def load():
     lib.orie_dcsb.restype = C.c_int
     lib.orie_dcsb.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     lib.orie_index_build.restype = C.c_int
-    lib.orie_index_build.argtypes = [i64, i64, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, C.POINTER(vp)]
+    lib.orie_index_build.argtypes = [i64, i64, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(Tuning), vp, vp,
+                                     C.POINTER(vp)]
+    lib.orie_index_status.restype = C.c_int
+    lib.orie_index_status.argtypes = [vp]
+    lib.orie_reward_workspace_bound.restype = C.c_size_t
+    lib.orie_reward_workspace_bound.argtypes = [vp, i64]
+    lib.orie_reward_depths.restype = C.c_int
+    lib.orie_reward_depths.argtypes = [vp, i64, i64, vp, i64, vp, C.c_size_t, vp, vp, vp]
+    lib.orie_rewards_from_sums.restype = C.c_int
+    lib.orie_rewards_from_sums.argtypes = [vp, i64, i32, i64, vp, vp]
     lib.orie_index_destroy.restype = None
     lib.orie_index_destroy.argtypes = [vp]
     lib.orie_index_info.restype = C.c_int

@@ -39,7 +39,7 @@ struct Dets {
 // ---- prep: one warp per (image, block) with block in {weak, strong, labels}.  Writes the image of every
 // row, the confidence sort keys, the class histograms (weak / labels drive the layouts, strong is only
 // range-checked), the per-image ground-truth class counts, and validates the inputs.
-//   status bit 0: an image has more than 65535 rows   bit 1: class id out of range   bit 2: off[M] != row count
+//   status bits (IndexMeta::status): kStatusRows, kStatusClass, kStatusCounts
 struct PrepArgs {
     int64_t M, C, Dw, Ds, G;
     const int64_t *w_off, *s_off, *l_off;
@@ -50,7 +50,7 @@ struct PrepArgs {
     uint32_t *img_l;     // [G]
     uint32_t *hist;      // [3][C]: weak, labels, strong
     uint32_t *gtcnt;     // [M][C], zero on entry
-    int32_t *status;
+    uint32_t *status;
     int smem_bins;       // 3 * C if the block-local histogram fits in shared memory, else 0
 };
 constexpr int kPrepThreads = 256;
@@ -62,19 +62,25 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepArgs a) {
     for (int i = threadIdx.x; i < a.smem_bins; i += kPrepThreads) bins[i] = 0;
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0 && (a.w_off[a.M] != a.Dw || a.s_off[a.M] != a.Ds || a.l_off[a.M] != a.G))
-        atomicOr(a.status, 4);
+        atomicOr(a.status, kStatusCounts);
     const int64_t nwarps = (int64_t)gridDim.x * (kPrepThreads / 32);
     for (int64_t w = (int64_t)blockIdx.x * (kPrepThreads / 32) + (threadIdx.x >> 5); w < 3 * a.M; w += nwarps) {
         const int blk = (int)(w / a.M);            // 0 weak, 1 labels, 2 strong (the order of the histograms)
         const int64_t im = w - blk * a.M;
         const int64_t *off = blk == 0 ? a.w_off : (blk == 1 ? a.l_off : a.s_off);
         const int32_t *cls = blk == 0 ? a.w_cls : (blk == 1 ? a.l_cls : a.s_cls);
-        const int64_t r0 = off[im], r1 = off[im + 1];
-        if (r1 - r0 > 65535 && lane == 0) atomicOr(a.status, 1);
+        const int64_t rows = blk == 0 ? a.Dw : (blk == 1 ? a.G : a.Ds);
+        int64_t r0 = off[im], r1 = off[im + 1];
+        if (r0 < 0 || r1 < r0 || r1 > rows) {        // inconsistent offsets: flag, and never read outside the arrays
+            if (lane == 0) atomicOr(a.status, kStatusCounts);
+            r1 = r1 < 0 ? 0 : (r1 > rows ? rows : r1);
+            r0 = r0 < 0 ? 0 : (r0 > r1 ? r1 : r0);
+        }
+        if (r1 - r0 > 65535 && lane == 0) atomicOr(a.status, kStatusRows);
         for (int64_t r = r0 + lane; r < r1; r += 32) {
             const int c = cls[r];
             const bool ok = c >= 0 && c < a.C;
-            if (!ok) atomicOr(a.status, 2);
+            if (!ok) atomicOr(a.status, kStatusClass);
             else if (a.smem_bins) atomicAdd(&bins[blk * a.C + c], 1u);
             else atomicAdd(&a.hist[blk * a.C + c], 1u);
             if (blk == 1) {
@@ -92,13 +98,70 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepArgs a) {
         if (bins[i]) atomicAdd(&a.hist[i], bins[i]);
 }
 
+// ---- layout: everything that follows from the class histograms, on the device (one CTA; the host used to read the
+// histograms back, lay the classes out and upload the tables — a synchronisation in the middle of every build).
+//   per class and stream: first row (cls_off), first slot of its padded range (pad_off), first segment (cls_seg0);
+//   per segment: first chunk and length in chunks; IndexMeta: slots / chunks / segments of both streams.
+// Detection stream: every class is padded to whole 32-slot chunks with at least one padding slot; label stream:
+// padded to whole chunks (a class without labels has no chunk and no segment).
+struct LayoutArgs {
+    int64_t C, S_cap, SL_cap;
+    int seg_chunks;
+    const uint32_t *hist;      // [3][C]: weak, labels, strong
+    uint32_t *cls_off, *pad_off, *lcls_off, *lpad_off;          // [C+1]
+    int32_t *cls_seg0, *lcls_seg0;                              // [C+1]
+    int32_t *seg_chunk0, *seg_nch, *lseg_chunk0, *lseg_nch;     // [S_cap], [SL_cap]
+    IndexMeta *meta;
+};
+constexpr int kLayoutThreads = 1024;
+
+__global__ void __launch_bounds__(kLayoutThreads) layout_kernel(const LayoutArgs a) {
+    __shared__ uint32_t ws[kLayoutThreads / 32];
+    const int tid = threadIdx.x;
+    uint32_t carry[2][3] = {{0, 0, 0}, {0, 0, 0}};      // rows, slots, segments in front of this tile, per stream
+    for (int64_t base = 0; base < a.C; base += kLayoutThreads) {
+        const int64_t c = base + tid;
+        const bool live = c < a.C;
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {                // 0: detections (extra padding slot), 1: labels
+            const uint32_t cnt = live ? a.hist[st * a.C + c] : 0u;
+            const uint32_t nch = live ? (cnt + (st == 0 ? 1u : 0u) + 31u) / 32u : 0u;
+            const uint32_t segs = (nch + (uint32_t)a.seg_chunks - 1u) / (uint32_t)a.seg_chunks;
+            uint32_t t_cnt, t_pad, t_seg;
+            const uint32_t x_cnt = carry[st][0] + block_exclusive_scan<kLayoutThreads>(cnt, ws, &t_cnt);
+            const uint32_t x_pad = carry[st][1] + block_exclusive_scan<kLayoutThreads>(nch * 32u, ws, &t_pad);
+            const uint32_t x_seg = carry[st][2] + block_exclusive_scan<kLayoutThreads>(segs, ws, &t_seg);
+            carry[st][0] += t_cnt; carry[st][1] += t_pad; carry[st][2] += t_seg;
+            if (live) {
+                (st == 0 ? a.cls_off : a.lcls_off)[c] = x_cnt;
+                (st == 0 ? a.pad_off : a.lpad_off)[c] = x_pad;
+                (st == 0 ? a.cls_seg0 : a.lcls_seg0)[c] = (int32_t)x_seg;
+                int32_t *chunk0 = st == 0 ? a.seg_chunk0 : a.lseg_chunk0, *len = st == 0 ? a.seg_nch : a.lseg_nch;
+                const int64_t cap = st == 0 ? a.S_cap : a.SL_cap;
+                for (uint32_t k = 0; k < segs; ++k) {
+                    if ((int64_t)(x_seg + k) >= cap) break;        // cannot happen: the capacities are upper bounds
+                    chunk0[x_seg + k] = (int32_t)(x_pad / 32u + k * (uint32_t)a.seg_chunks);
+                    len[x_seg + k] = (int32_t)min((uint32_t)a.seg_chunks, nch - k * (uint32_t)a.seg_chunks);
+                }
+            }
+        }
+    }
+    if (tid == 0) {
+        a.cls_off[a.C] = carry[0][0]; a.pad_off[a.C] = carry[0][1]; a.cls_seg0[a.C] = (int32_t)carry[0][2];
+        a.lcls_off[a.C] = carry[1][0]; a.lpad_off[a.C] = carry[1][1]; a.lcls_seg0[a.C] = (int32_t)carry[1][2];
+        a.meta->P = carry[0][1]; a.meta->nchunks = carry[0][1] / 32u; a.meta->S = carry[0][2];
+        a.meta->PL = carry[1][1]; a.meta->nchunksL = carry[1][1] / 32u; a.meta->SL = carry[1][2];
+    }
+}
+
 // ----------------------------------------------------------------------------
-// Everything after the host has laid out the classes, in ONE cooperative launch (three phases separated by grid
-// barriers; eight dependent launches of a few microseconds each before, whose enqueue cost exceeded their run time):
+// Everything after the sorts, in ONE cooperative launch (four phases separated by grid barriers; eight dependent
+// launches of a few microseconds each before, whose enqueue cost exceeded their run time):
 //   A  padding slots of both streams (image M = never a member, no true positive); position v of the combined
 //      (class, conf desc) order -> slot (weak) / insertion slot (strong) [wpre[v] = weak detections sorted before v];
 //      labels into the class-major label stream (only the grouping by class matters — the label walk counts members
-//      per class — so a label takes the next free slot of its class)
+//      per class — so a label takes the next free slot of its class); classes ranked by weak-detection count
+//      (cls_order, by counting)
 //   B  event counts per CTA range of chunks (event = slot holding a true positive);
 //      own lists: the rows of one image and detector in (class, conf) order, i.e. ascending by their position in the
 //      global order — an image has a few hundred rows at most in practice, so one warp ranks them by counting instead
@@ -106,14 +169,16 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepArgs a) {
 //      class >= c, c in [0, C];
 //      bqoff[b][s] = first query of batch b with slot >= first slot of segment s (searched through the batch-major
 //      order and the slots of phase A)
-//   C  evbase = events in front of every chunk (exclusive scan), their total, each segment's first event; per-batch
-//      query list: position v of the batch-major order IS the entry, ascending by slot, weak and strong interleaved
+//   C  events in front of every chunk / segment (exclusive scan) and their total; per-batch query list: position v
+//      of the batch-major order IS the entry, ascending by slot, weak and strong interleaved
+//   D  per image the classes in which it has a detection from either detector, deepest AP sweep first (act_cls)
+// The sizes that depend on the data (slots, chunks, segments) are read from IndexMeta, written by layout_kernel.
 // Arrays written in one phase and read in a later one are read with __ldcg (L2), never through the read-only path.
 // ----------------------------------------------------------------------------
 struct PostArgs {
     Dets d;
-    int64_t n, M, C, G, P, PL, nchunks, S, nbatch, ev_per;
-    const uint32_t *order, *wpre, *img_all, *ord_bat, *img_l;
+    int64_t n, M, C, G, nbatch, S_cap;
+    const uint32_t *order, *wpre, *img_all, *ord_bat, *img_l, *hist;
     const int32_t *l_cls, *seg_chunk0;
     const uint32_t *cls_off, *pad_off, *lcls_off, *lpad_off;
     const int64_t *w_off, *s_off;
@@ -123,8 +188,13 @@ struct PostArgs {
     uint32_t *q_of_det, *pos_of_det, *ownpos;
     uint32_t *own_w_q, *own_s_q;
     uint16_t *own_w_m, *own_s_m, *own_w_c, *own_s_c, *own_w_cs, *own_s_cs;
+    int32_t *cls_order;
+    uint16_t *act_cls;
+    uint32_t *nact, *evbase, *act_key;
+    uint16_t *act_tmp;
     uint2 *bq;
-    uint32_t *bqoff, *evbase, *seg_ev0, *table, *total_out;
+    uint32_t *bqoff, *seg_ev0, *table;
+    IndexMeta *meta;
     unsigned *bar;
 };
 constexpr int kPostThreads = 256;
@@ -139,6 +209,9 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
     const int64_t gsize = (int64_t)gridDim.x * kPostThreads;
     const int64_t gwarp = gtid >> 5, nwarps = gsize >> 5;
     unsigned epoch = 0;
+    // invalid input (flagged by prep_kernel): class ids may be out of range, nothing below is safe — every CTA leaves
+    if (a.meta->status & (kStatusRows | kStatusClass | kStatusCounts)) return;
+    const int64_t nchunks = a.meta->nchunks, S = a.meta->S;
 
     // ---- A
     for (int64_t k = gtid; k < a.C * 64; k += gsize) {           // at most 32 padding slots per class and stream
@@ -166,12 +239,22 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
         const int c = a.l_cls[g];
         a.lab_slot_img[a.lpad_off[c] + atomicAdd(&a.lcursor[c], 1u)] = a.img_l[g];
     }
+    for (int64_t c = gtid; c < a.C; c += gsize) {                // stable rank by descending weak-detection count
+        const uint32_t h = a.hist[c];
+        uint32_t rank = 0;
+        for (int64_t o = 0; o < a.C; ++o) {
+            const uint32_t ho = a.hist[o];
+            rank += (ho > h || (ho == h && o < c)) ? 1u : 0u;
+        }
+        a.cls_order[rank] = (int32_t)c;
+    }
     grid_sync(a.bar, epoch);
 
     // ---- B: events of this CTA's chunk range, split over its warps
-    const int64_t c0 = (int64_t)blockIdx.x * a.ev_per, c1 = c0 + a.ev_per < a.nchunks ? c0 + a.ev_per : a.nchunks;
-    const int64_t cw = (a.ev_per + kPostWarps - 1) / kPostWarps;
-    const int64_t w0 = c0 + warp * cw, w1 = w0 + cw < c1 ? w0 + cw : c1;
+    const int64_t ev_per = (nchunks + gridDim.x - 1) / gridDim.x;
+    const int64_t c0 = min((int64_t)blockIdx.x * ev_per, nchunks), c1 = min(c0 + ev_per, nchunks);
+    const int64_t cw = (ev_per + kPostWarps - 1) / kPostWarps;
+    const int64_t w0 = min(c0 + warp * cw, c1), w1 = min(w0 + cw, c1);
     uint32_t mine = 0;
     for (int64_t ch = w0; ch < w1; ++ch) mine += __popc(__ballot_sync(kFull, __ldcg(a.slot_tp + ch * 32 + lane) != 0));
     uint32_t cta_total;
@@ -231,11 +314,11 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
             row[c] = (uint16_t)lo;
         }
     }
-    for (int64_t k = gtid; k < a.nbatch * (a.S + 1); k += gsize) {
-        const int64_t b = k / (a.S + 1), s = k % (a.S + 1);
+    for (int64_t k = gtid; k < a.nbatch * (a.S_cap + 1); k += gsize) {
+        const int64_t b = k / (a.S_cap + 1), s = k % (a.S_cap + 1);
         const int64_t i0 = b * 32 < a.M ? b * 32 : a.M, i1 = (b + 1) * 32 < a.M ? (b + 1) * 32 : a.M;
         int64_t lo = a.w_off[i0] + a.s_off[i0], hi = a.w_off[i1] + a.s_off[i1];
-        if (s < a.S) {
+        if (s < S) {
             const uint32_t slot0 = (uint32_t)a.seg_chunk0[s] * 32u;
             while (lo < hi) {
                 const int64_t mid = (lo + hi) >> 1;
@@ -259,18 +342,18 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
         uint32_t carry, grand;
         block_exclusive_scan<kPostThreads>(before, ws, &carry);
         block_exclusive_scan<kPostThreads>(all, ws, &grand);
-        if (blockIdx.x == 0 && threadIdx.x == 0) *a.total_out = grand;
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.meta->Ev = grand;
         uint32_t run = carry + warp_base;
         for (int64_t ch = w0; ch < w1; ++ch) {
             const unsigned b = __ballot_sync(kFull, __ldcg(a.slot_tp + ch * 32 + lane) != 0);
             if (lane == 0) {
-                a.evbase[ch] = run;
-                int64_t lo = 0, hi = a.S;                  // is this chunk the first of a segment?
+                __stcg(a.evbase + ch, run);
+                int64_t lo = 0, hi = S;                    // is this chunk the first of a segment?
                 while (lo < hi) {
                     const int64_t mid = (lo + hi) >> 1;
                     if (a.seg_chunk0[mid] < ch) lo = mid + 1; else hi = mid;
                 }
-                if (lo < a.S && a.seg_chunk0[lo] == ch) a.seg_ev0[lo] = run;
+                if (lo < S && a.seg_chunk0[lo] == ch) a.seg_ev0[lo] = run;
             }
             run += __popc(b);
         }
@@ -279,6 +362,66 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
         const uint32_t u = a.ord_bat[v];
         a.bq[v] = make_uint2(__ldcg(a.q_of_det + u) | (u >= a.d.Dw ? 0x80000000u : 0u),
                              ((a.img_all[u] & 31u) << 27) | __ldcg(a.ownpos + u));
+    }
+    grid_sync(a.bar, epoch);
+
+    // ---- D: per image the classes in which it has a detection from either detector, ordered by how deep the AP
+    //      sweep of the class will go for this image as a target: the reverse sweep runs from the class's lowest
+    //      confidence up to the image's most confident own detection, so its length is proportional to the number
+    //      of events (true positives of the dataset) behind that detection.  The AP kernel gives neighbouring entries
+    //      to the lanes of one warp, so lanes that work side by side stop at about the same time.
+    for (int64_t im = gwarp; im < a.M; im += nwarps) {
+        const uint16_t *wcs = a.own_w_cs + im * (a.C + 1), *scs = a.own_s_cs + im * (a.C + 1);
+        const uint32_t *wq = a.own_w_q + a.w_off[im], *sq = a.own_s_q + a.s_off[im];
+        uint16_t *tmp = a.act_tmp + im * a.C, *out = a.act_cls + im * a.C;
+        uint32_t *key = a.act_key + im * a.C;
+        uint32_t n = 0;
+        for (int64_t ci0 = 0; ci0 < a.C; ci0 += 32) {
+            const int64_t ci = ci0 + lane;
+            int c = 0;
+            bool act = false;
+            uint32_t depth = 0;
+            if (ci < a.C) {
+                c = __ldcg(a.cls_order + ci);
+                const int w0c = __ldcg(wcs + c), w1c = __ldcg(wcs + c + 1), s0c = __ldcg(scs + c), s1c = __ldcg(scs + c + 1);
+                act = w1c > w0c || s1c > s0c;
+                if (act) {
+                    // own lists are (class, confidence desc): the first entry of the class is its most confident row
+                    uint32_t q = 0xffffffffu;
+                    if (w1c > w0c) q = min(q, __ldcg(wq + w0c));
+                    if (s1c > s0c) q = min(q, __ldcg(sq + s0c));
+                    const uint32_t last = a.pad_off[c + 1] / 32u - 1u;           // last chunk of the class (padding: no events)
+                    const uint32_t ch = min(q / 32u, last);
+                    depth = __ldcg(a.evbase + last) - __ldcg(a.evbase + ch);
+                }
+            }
+            const unsigned b = __ballot_sync(kFull, act);
+            if (act) {
+                const uint32_t at = n + __popc(b & ((1u << lane) - 1u));
+                tmp[at] = (uint16_t)c;
+                key[at] = depth;
+            }
+            n += __popc(b);
+        }
+        __syncwarp();
+        const bool fits = n <= (uint32_t)kRankStage;
+        if (fits)
+            for (uint32_t k = lane; k < n; k += 32) staged[warp][k] = key[k];
+        __syncwarp();
+        for (uint32_t e0 = 0; e0 < n; e0 += 32) {           // stable rank by descending depth, by counting
+            const uint32_t e = e0 + lane;
+            if (e < n) {
+                const uint32_t me = fits ? staged[warp][e] : key[e];
+                uint32_t rank = 0;
+                for (uint32_t o = 0; o < n; ++o) {
+                    const uint32_t ko = fits ? staged[warp][o] : key[o];
+                    rank += (ko > me || (ko == me && o < e)) ? 1u : 0u;
+                }
+                out[rank] = tmp[e];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) a.nact[im] = n;
     }
 }
 
@@ -291,9 +434,13 @@ static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
 // The index's memory comes from a stream-ordered pool that is PRIVATE to this library (one per device, created on
 // first use, never trimmed so that rebuilding an index does not go back to the driver).  The device's default pool
 // — which the host application may be using — is never touched.
-static int engine_pool(cudaMemPool_t *out) {
+struct DeviceState {
+    cudaMemPool_t pool = nullptr;
+    int sort_blocks = 0, post_blocks = 0, sms = 0;
+};
+static int device_state(DeviceState **out) {
     static std::mutex mu;
-    static cudaMemPool_t pools[64] = {};
+    static DeviceState states[64];
     int dev = 0;
     ORIE_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) {
@@ -301,7 +448,8 @@ static int engine_pool(cudaMemPool_t *out) {
         return ORIE_ELIMIT;
     }
     std::lock_guard<std::mutex> lock(mu);
-    if (!pools[dev]) {
+    DeviceState &s = states[dev];
+    if (!s.pool) {
         cudaMemPoolProps props = {};
         props.allocType = cudaMemAllocationTypePinned;
         props.handleTypes = cudaMemHandleTypeNone;
@@ -311,9 +459,12 @@ static int engine_pool(cudaMemPool_t *out) {
         ORIE_CUDA(cudaMemPoolCreate(&pool, &props));
         uint64_t keep_all = UINT64_MAX;
         ORIE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
-        pools[dev] = pool;
+        ORIE_CUDA(cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev));
+        ORIE_TRY(sort_max_blocks(&s.sort_blocks));
+        ORIE_TRY(coop_max_blocks(post_kernel, kPostThreads, 0, &s.post_blocks));
+        s.pool = pool;
     }
-    *out = pools[dev];
+    *out = &s;
     return ORIE_OK;
 }
 
@@ -328,12 +479,10 @@ struct Arena {
     void add(Tp **p, int64_t count) {
         items.push_back({(void **)p, (size_t)round_up(std::max<int64_t>(count, 1) * (int64_t)sizeof(Tp), 256)});
     }
-    int commit(cudaStream_t st, void **base, size_t *bytes) {
+    int commit(cudaMemPool_t pool, cudaStream_t st, void **base, size_t *bytes) {
         size_t total = 0;
         for (auto &it : items) total += it.bytes;
         void *q = nullptr;
-        cudaMemPool_t pool;
-        ORIE_TRY(engine_pool(&pool));
         ORIE_CUDA(cudaMallocFromPoolAsync(&q, std::max<size_t>(total, 256), pool, st));
         size_t at = 0;
         for (auto &it : items) {
@@ -347,108 +496,57 @@ struct Arena {
     }
 };
 
-struct Builder {
-    orie_index *ix;
+// Frees the temporaries in stream order when the build function returns, on success and on error alike.
+struct TempGuard {
     cudaStream_t st;
-    void *temp_base = nullptr;
-    ~Builder() {
-        cudaStreamSynchronize(st);
-        if (temp_base) cudaFreeAsync(temp_base, st);
-    }
-    int keep(Arena &a) {
-        void *base = nullptr;
-        size_t bytes = 0;
-        ORIE_TRY(a.commit(st, &base, &bytes));
-        ix->allocs[ix->n_allocs++] = base;      // at most three arenas per index
-        ix->device_bytes += (int64_t)bytes;
-        return ORIE_OK;
+    void *base = nullptr;
+    ~TempGuard() {
+        if (base) cudaFreeAsync(base, st);
     }
 };
 
-static inline unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)std::max<int64_t>(ceil_div(n, threads), 1); }
-
-// Padded layout of one class-sorted stream on the host: per class padded length, then segments.
-struct StreamLayout {
-    std::vector<uint32_t> cls_off, pad_off;
-    std::vector<int32_t> seg_chunk0, seg_nch, cls_seg0;
-    int64_t P = 0;
-};
-
-static StreamLayout make_layout(const uint32_t *cnt, int64_t C, int extra_pad, int seg_chunks) {
-    StreamLayout L;
-    L.cls_off.resize(C + 1);
-    L.pad_off.resize(C + 1);
-    L.cls_seg0.resize(C + 1);
-    uint32_t a = 0, p = 0;
-    for (int64_t c = 0; c < C; ++c) {
-        L.cls_off[c] = a;
-        L.pad_off[c] = p;
-        L.cls_seg0[c] = (int32_t)L.seg_chunk0.size();
-        const int64_t padlen = round_up((int64_t)cnt[c] + extra_pad, kChunk);
-        const int nch = (int)(padlen / kChunk);
-        for (int k = 0; k < nch; k += seg_chunks) {
-            L.seg_chunk0.push_back((int32_t)(p / kChunk) + k);
-            L.seg_nch.push_back(std::min(seg_chunks, nch - k));
-        }
-        a += cnt[c];
-        p += (uint32_t)padlen;
-    }
-    L.cls_off[C] = a;
-    L.pad_off[C] = p;
-    L.cls_seg0[C] = (int32_t)L.seg_chunk0.size();
-    L.P = p;
-    return L;
-}
-
-// the host-built tables travel in one buffer / one copy
-struct Tables {
-    std::vector<uint32_t> words;
-    struct Ref {
-        void **p;
-        size_t at;
-    };
-    std::vector<Ref> refs;
-    template <typename Tp, typename Vp>
-    void add(Tp **p, const std::vector<Vp> &v) {
-        static_assert(sizeof(Vp) == 4, "32-bit tables only");
-        refs.push_back({(void **)p, words.size()});
-        const size_t n = v.size();
-        words.resize(words.size() + (size_t)round_up(std::max<int64_t>((int64_t)n, 1), 64));
-        if (n) memcpy(words.data() + refs.back().at, v.data(), n * 4);
-    }
-    void bind(uint32_t *base) {
-        for (auto &r : refs) *r.p = base + r.at;
-    }
-};
-
+// The whole build is enqueued on `st` without a single host synchronisation: allocation sizes, launch grids and table
+// strides come from upper bounds the host can compute from (M, C, Dw, Ds, G); what depends on the data stays on the
+// device (IndexMeta).
 static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                  const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
-                 const int64_t *l_off, const int32_t *l_cls, int seg_chunks_req, cudaEvent_t tp_ready, cudaStream_t st) {
-    // host staging buffers are declared before the Builder so that they outlive its destructor, which
-    // synchronises the stream (asynchronous copies from / into them may still be in flight on error paths)
+                 const int64_t *l_off, const int32_t *l_cls, const orie_tuning_t &tune, cudaEvent_t tp_ready, cudaStream_t st) {
     const int64_t M = ix->M, C = ix->C;
-    std::vector<uint32_t> h_meta(3 * C + 1);
-    std::vector<int32_t> cls_order(C);
-    StreamLayout LD, LL;
-    Tables tab;
-    uint32_t h_total = 0;
-    Builder B{ix, st};
-    // ---- sizes: given by the caller; off[M] of each block is cross-checked on the device (status bit 2)
     const int64_t Dw = ix->Dw, Ds = ix->Ds, G = ix->G;
     if (Dw < 0 || Ds < 0 || G < 0 || Dw >= ((int64_t)1 << 27) || Ds >= ((int64_t)1 << 27) || G >= ((int64_t)1 << 31)) {
         set_error("orie_index_build: row counts out of range (weak %lld, strong %lld, labels %lld; limit 2^27-1 detections per detector)",
                   (long long)Dw, (long long)Ds, (long long)G);
         return ORIE_ELIMIT;
     }
+    DeviceState *ds = nullptr;
+    ORIE_TRY(device_state(&ds));
     const int64_t n = Dw + Ds;
     const int64_t Nmax = std::max<int64_t>(std::max(n, G), 1);
     const Dets dets{Dw, Ds, w_cls, s_cls, w_conf, s_conf, w_tp, s_tp};
-    int sort_blocks = 0, post_blocks = 0;
-    ORIE_TRY(sort_max_blocks(&sort_blocks));
-    ORIE_TRY(coop_max_blocks(post_kernel, kPostThreads, 0, &post_blocks));
+    int sort_blocks = ds->sort_blocks, post_blocks = ds->post_blocks;
+    if (tune.sort_max_blocks > 0) sort_blocks = std::min(sort_blocks, tune.sort_max_blocks);
 
-    // ---- first part of the index (sizes known up front) and the temporaries, one allocation each
+    // ---- capacities.  Detection stream: class c takes ceil((cnt_c + 1) / 32) <= cnt_c / 32 + 1 chunks; label stream:
+    //      ceil(cnt_c / 32).  A class of nch chunks has ceil(nch / seg_chunks) <= nch / seg_chunks + 1 segments.
+    const int64_t chunks_cap = Dw / 32 + C, chunksL_cap = G / 32 + C;
+    // Segment length: about two segments per average class (measured best for both the walk's load balance and the
+    // AP sweep on COCO-shaped data, profiles/), enough (batch, segment) warp items for >= 4 waves of 148 SMs x 8
+    // warps, and no segment so long that a single warp becomes the tail of the walk.  An event record keeps its rank
+    // inside the segment in 16 bits: at most 2047 chunks = 65504 slots per segment.
+    const int64_t seg_target = std::max<int64_t>(2 * C, ceil_div(4 * 148 * 8, ix->nbatch));
+    const int seg_chunks = tune.seg_chunks > 0 ? std::min(tune.seg_chunks, 2047)
+                                               : (int)std::min<int64_t>(512, std::max<int64_t>(16, ceil_div(chunks_cap, seg_target)));
+    ix->seg_chunks = seg_chunks;
+    ix->nchunks_cap = chunks_cap;
+    ix->P_cap = chunks_cap * kChunk;
+    ix->S_cap = chunks_cap / seg_chunks + C + 1;
+    ix->PL_cap = chunksL_cap * kChunk;
+    ix->SL_cap = chunksL_cap / seg_chunks + C + 1;
+    ix->Ev_cap = std::min<int64_t>(Dw, G * ix->T);     // a label is claimed by at most one detection per threshold
+
+    // ---- the index and the temporaries, one allocation each
     Arena A;
+    A.add(&ix->meta, 1);
     A.add(&ix->w_off, M + 1);
     A.add(&ix->s_off, M + 1);
     A.add(&ix->own_w_q, Dw);
@@ -457,14 +555,37 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&ix->own_s_m, Ds);
     A.add(&ix->own_w_cs, M * (C + 1));
     A.add(&ix->own_s_cs, M * (C + 1));
+    A.add(&ix->act_cls, M * C);
+    A.add(&ix->nact, M);
     A.add(&ix->bq, n);
     A.add(&ix->gtcnt, M * C);
-    ORIE_TRY(B.keep(A));
+    A.add(&ix->slot_img, ix->P_cap);
+    A.add(&ix->slot_tp, ix->P_cap);
+    A.add(&ix->seg_chunk0, ix->S_cap);
+    A.add(&ix->seg_nch, ix->S_cap);
+    A.add(&ix->seg_ev0, ix->S_cap);
+    A.add(&ix->cls_seg0, C + 1);
+    A.add(&ix->cls_order, C);
+    A.add(&ix->bqoff, ix->nbatch * (ix->S_cap + 1));
+    A.add(&ix->lab_slot_img, ix->PL_cap);
+    A.add(&ix->lseg_chunk0, ix->SL_cap);
+    A.add(&ix->lseg_nch, ix->SL_cap);
+    A.add(&ix->lcls_seg0, C + 1);
+    {
+        void *base = nullptr;
+        size_t bytes = 0;
+        ORIE_TRY(A.commit(ds->pool, st, &base, &bytes));
+        ix->allocs[ix->n_allocs++] = base;
+        ix->device_bytes += (int64_t)bytes;
+    }
 
     uint64_t *keys, *keys_tmp;
-    uint32_t *vtmp, *img_all, *img_l, *order, *ord_bat, *pos_of_det, *lcursor, *meta, *wpre, *q_of_det, *ownpos, *d_total;
-    uint16_t *own_w_c, *own_s_c;
+    uint32_t *vtmp, *img_all, *img_l, *order, *ord_bat, *pos_of_det, *lcursor, *hist, *wpre, *q_of_det, *ownpos;
+    uint32_t *d_cls_off, *d_pad_off, *d_lcls_off, *d_lpad_off;
+    uint16_t *own_w_c, *own_s_c, *act_tmp;
+    uint32_t *evbase, *act_key;
     char *scratch;
+    TempGuard temp{st};
     A.add(&keys, n);
     A.add(&keys_tmp, n);
     A.add(&vtmp, Nmax);
@@ -474,20 +595,26 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&ord_bat, n);
     A.add(&pos_of_det, n);
     A.add(&lcursor, C);
-    A.add(&meta, 3 * C + 1);
+    A.add(&hist, 3 * C);
     A.add(&wpre, n);
     A.add(&q_of_det, n);
     A.add(&ownpos, n);
     A.add(&own_w_c, Dw);
     A.add(&own_s_c, Ds);
-    A.add(&d_total, 1);
+    A.add(&act_tmp, M * C);
+    A.add(&act_key, M * C);
+    A.add(&evbase, ix->nchunks_cap);
+    A.add(&d_cls_off, C + 1);
+    A.add(&d_pad_off, C + 1);
+    A.add(&d_lcls_off, C + 1);
+    A.add(&d_lpad_off, C + 1);
     A.add(&scratch, (int64_t)std::max(sort_scratch_bytes(sort_blocks), (size_t)post_blocks * 4 + 256));
-    ORIE_TRY(A.commit(st, &B.temp_base, nullptr));
-    int32_t *status = (int32_t *)(meta + 3 * C);
+    ORIE_TRY(A.commit(ds->pool, st, &temp.base, nullptr));
 
     ORIE_CUDA(cudaMemcpyAsync(ix->w_off, w_off, (size_t)(M + 1) * 8, cudaMemcpyDeviceToDevice, st));
     ORIE_CUDA(cudaMemcpyAsync(ix->s_off, s_off, (size_t)(M + 1) * 8, cudaMemcpyDeviceToDevice, st));
-    ORIE_CUDA(cudaMemsetAsync(meta, 0, (size_t)(3 * C + 1) * 4, st));
+    ORIE_CUDA(cudaMemsetAsync(ix->meta, 0, sizeof(IndexMeta), st));
+    ORIE_CUDA(cudaMemsetAsync(hist, 0, (size_t)(3 * C) * 4, st));
     ORIE_CUDA(cudaMemsetAsync(ix->gtcnt, 0, (size_t)(M * C) * 4, st));
     ORIE_CUDA(cudaMemsetAsync(lcursor, 0, (size_t)C * 4, st));
 
@@ -496,9 +623,16 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     // ---- prep: images of rows, confidence keys, class histograms, ground-truth counts, validation
     {
         PrepArgs pa{M, C, Dw, Ds, G, w_off, s_off, l_off, w_cls, s_cls, l_cls, w_conf, s_conf,
-                    keys, img_all, img_l, meta, ix->gtcnt, status, 3 * C <= kPrepMaxSmemBins ? (int)(3 * C) : 0};
+                    keys, img_all, img_l, hist, ix->gtcnt, &ix->meta->status, 3 * C <= kPrepMaxSmemBins ? (int)(3 * C) : 0};
         const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(3 * M, kPrepThreads / 32), 148 * 8);
         prep_kernel<<<grid, kPrepThreads, (size_t)pa.smem_bins * 4, st>>>(pa);
+        ORIE_LAUNCH_CHECK();
+    }
+    // ---- layout: class counts -> padded layouts and segment tables, on the device
+    {
+        LayoutArgs la{C, ix->S_cap, ix->SL_cap, seg_chunks, hist, d_cls_off, d_pad_off, d_lcls_off, d_lpad_off,
+                      ix->cls_seg0, ix->lcls_seg0, ix->seg_chunk0, ix->seg_nch, ix->lseg_chunk0, ix->lseg_nch, ix->meta};
+        layout_kernel<<<1, kLayoutThreads, 0, st>>>(la);
         ORIE_LAUNCH_CHECK();
     }
 
@@ -525,79 +659,14 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         ORIE_TRY(sort_run(r, sort_blocks, scratch, st));
     }
 
-    // ---- host: class counts -> padded layouts and segment tables
-    ORIE_CUDA(cudaMemcpyAsync(h_meta.data(), meta, (size_t)(3 * C + 1) * 4, cudaMemcpyDeviceToHost, st));
-    ORIE_CUDA(cudaStreamSynchronize(st));
-    const uint32_t h_status = h_meta[3 * C];
-    if (h_status & 4) {
-        set_error("orie_index_build: row counts (%lld, %lld, %lld) do not match the offset arrays",
-                  (long long)Dw, (long long)Ds, (long long)G);
-        return ORIE_EDATA;
-    }
-    if (h_status & 2) {
-        set_error("orie_index_build: class id outside [0, %lld)", (long long)C);
-        return ORIE_EDATA;
-    }
-    if (h_status & 1) {
-        set_error("orie_index_build: an image has more than 65535 rows in one file");
-        return ORIE_ELIMIT;
-    }
-    const uint32_t *h_hist = h_meta.data();
-    int64_t raw_chunks = 0;
-    for (int64_t c = 0; c < C; ++c) raw_chunks += ceil_div((int64_t)h_hist[c] + 1, kChunk);
-    // Segment length: about two segments per average class (measured best for both the walk's load balance
-    // and the AP sweep on COCO-shaped data, profiles/), enough (batch, segment) warp items for >= 4 waves of
-    // 148 SMs x 8 warps, and no segment so long that a single warp becomes the tail of the walk.
-    const int64_t seg_target = std::max<int64_t>(2 * C, ceil_div(4 * 148 * 8, ix->nbatch));
-    // (an event record keeps its rank inside the segment in 16 bits: at most 2047 chunks = 65504 slots per segment)
-    int seg_chunks = seg_chunks_req > 0 ? std::min(seg_chunks_req, 2047)
-                                        : (int)std::min<int64_t>(512, std::max<int64_t>(16, ceil_div(raw_chunks, seg_target)));
-    ix->seg_chunks = seg_chunks;
-    LD = make_layout(h_hist, C, 1, seg_chunks);
-    LL = make_layout(h_hist + C, C, 0, seg_chunks);
-    ix->P = LD.P; ix->nchunks = LD.P / kChunk; ix->S = (int64_t)LD.seg_chunk0.size();
-    ix->PL = LL.P; ix->nchunksL = LL.P / kChunk; ix->SL = (int64_t)LL.seg_chunk0.size();
-    if (ix->P >= ((int64_t)1 << 31)) {
-        set_error("orie_index_build: %lld slots exceed 2^31-1", (long long)ix->P);
-        return ORIE_ELIMIT;
-    }
-    for (int64_t c = 0; c < C; ++c) cls_order[c] = (int32_t)c;
-    std::stable_sort(cls_order.begin(), cls_order.end(), [&](int32_t a, int32_t b) { return h_hist[a] > h_hist[b]; });
-    uint32_t *d_cls_off, *d_pad_off, *d_lcls_off, *d_lpad_off, *d_tables;
-    tab.add(&d_cls_off, LD.cls_off);
-    tab.add(&d_pad_off, LD.pad_off);
-    tab.add(&d_lcls_off, LL.cls_off);
-    tab.add(&d_lpad_off, LL.pad_off);
-    tab.add(&ix->seg_chunk0, LD.seg_chunk0);
-    tab.add(&ix->seg_nch, LD.seg_nch);
-    tab.add(&ix->cls_seg0, LD.cls_seg0);
-    tab.add(&ix->cls_order, cls_order);
-    tab.add(&ix->lseg_chunk0, LL.seg_chunk0);
-    tab.add(&ix->lseg_nch, LL.seg_nch);
-    tab.add(&ix->lcls_seg0, LL.cls_seg0);
-
-    // ---- second part of the index (sizes depend on the class counts)
-    A.add(&d_tables, (int64_t)tab.words.size());
-    A.add(&ix->slot_img, ix->P);
-    A.add(&ix->slot_tp, ix->P);
-    A.add(&ix->evbase, ix->nchunks);
-    A.add(&ix->seg_ev0, ix->S);
-    A.add(&ix->bqoff, ix->nbatch * (ix->S + 1));
-    A.add(&ix->lab_slot_img, ix->PL);
-    ORIE_TRY(B.keep(A));
-    tab.bind(d_tables);
-    ORIE_CUDA(cudaMemcpyAsync(d_tables, tab.words.data(), tab.words.size() * 4, cudaMemcpyHostToDevice, st));
-    // tab.words stays alive until the end of this function, which ends with a stream synchronisation
-
     // ---- everything else in one cooperative launch (post_kernel)
     if (tp_ready) ORIE_CUDA(cudaStreamWaitEvent(st, tp_ready, 0));     // first reader of the true-positive masks
     {
         PostArgs pa;
         memset(&pa, 0, sizeof(pa));
         pa.d = dets;
-        pa.n = n; pa.M = M; pa.C = C; pa.G = G; pa.P = ix->P; pa.PL = ix->PL; pa.nchunks = ix->nchunks; pa.S = ix->S;
-        pa.nbatch = ix->nbatch;
-        pa.order = order; pa.wpre = wpre; pa.img_all = img_all; pa.ord_bat = ord_bat; pa.img_l = img_l;
+        pa.n = n; pa.M = M; pa.C = C; pa.G = G; pa.nbatch = ix->nbatch; pa.S_cap = ix->S_cap;
+        pa.order = order; pa.wpre = wpre; pa.img_all = img_all; pa.ord_bat = ord_bat; pa.img_l = img_l; pa.hist = hist;
         pa.l_cls = l_cls; pa.seg_chunk0 = ix->seg_chunk0;
         pa.cls_off = d_cls_off; pa.pad_off = d_pad_off; pa.lcls_off = d_lcls_off; pa.lpad_off = d_lpad_off;
         pa.w_off = ix->w_off; pa.s_off = ix->s_off;
@@ -606,29 +675,51 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         pa.q_of_det = q_of_det; pa.pos_of_det = pos_of_det; pa.ownpos = ownpos;
         pa.own_w_q = ix->own_w_q; pa.own_s_q = ix->own_s_q; pa.own_w_m = ix->own_w_m; pa.own_s_m = ix->own_s_m;
         pa.own_w_c = own_w_c; pa.own_s_c = own_s_c; pa.own_w_cs = ix->own_w_cs; pa.own_s_cs = ix->own_s_cs;
-        pa.bq = ix->bq; pa.bqoff = ix->bqoff; pa.evbase = ix->evbase; pa.seg_ev0 = ix->seg_ev0;
+        pa.cls_order = ix->cls_order; pa.act_cls = ix->act_cls; pa.nact = ix->nact;
+        pa.evbase = evbase; pa.act_key = act_key; pa.act_tmp = act_tmp;
+        pa.bq = ix->bq; pa.bqoff = ix->bqoff; pa.seg_ev0 = ix->seg_ev0;
+        pa.meta = ix->meta;
         pa.bar = (unsigned *)scratch;
         pa.table = (uint32_t *)(scratch + 256);
-        pa.total_out = d_total;
         // three CTAs per SM: more only make the grid barriers dearer (measured, profiles/)
-        {
-            int dev = 0, sms = 0;
-            ORIE_CUDA(cudaGetDevice(&dev));
-            ORIE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            post_blocks = std::min(post_blocks, 3 * sms);
-        }
-        if (const char *cap = getenv("ORIE_POST_BLOCKS")) post_blocks = std::max(1, std::min(post_blocks, atoi(cap)));   // developer knob
-        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(post_blocks, ceil_div(std::max(n, ix->P), kPostThreads)));
-        pa.ev_per = ceil_div(std::max<int64_t>(ix->nchunks, 1), blocks);
+        post_blocks = std::min(post_blocks, 3 * ds->sms);
+        if (tune.post_blocks > 0) post_blocks = std::max(1, std::min(post_blocks, tune.post_blocks));
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(post_blocks, ceil_div(std::max(n, ix->P_cap), kPostThreads)));
         ORIE_CUDA(cudaMemsetAsync(pa.bar, 0, 4, st));
         void *args[] = {&pa};
         ORIE_CUDA(cudaLaunchCooperativeKernel((const void *)post_kernel, dim3(blocks), dim3(kPostThreads), args, 0, st));
         ORIE_LAUNCH_CHECK();
-        ORIE_CUDA(cudaMemcpyAsync(&h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
     }
-    ORIE_CUDA(cudaStreamSynchronize(st));
-    ix->Ev = h_total;
+    ORIE_CUDA(cudaEventRecord(ix->ready, st));
     return ORIE_OK;
+}
+
+int resolve(const orie_index *cix) {
+    orie_index *ix = const_cast<orie_index *>(cix);
+    if (ix->resolved) {
+        if (ix->resolved_rc != ORIE_OK) set_error("orie_index: the build of this index failed (code %d)", ix->resolved_rc);
+        return ix->resolved_rc;
+    }
+    IndexMeta m;
+    ORIE_CUDA(cudaEventSynchronize(ix->ready));
+    ORIE_CUDA(cudaMemcpy(&m, ix->meta, sizeof(m), cudaMemcpyDeviceToHost));
+    ix->P = m.P; ix->nchunks = m.nchunks; ix->S = m.S; ix->Ev = m.Ev;
+    ix->PL = m.PL; ix->nchunksL = m.nchunksL; ix->SL = m.SL;
+    int rc = ORIE_OK;
+    if (m.status & kStatusCounts) {
+        set_error("orie_index_build: row counts (%lld, %lld, %lld) do not match the offset arrays",
+                  (long long)ix->Dw, (long long)ix->Ds, (long long)ix->G);
+        rc = ORIE_EDATA;
+    } else if (m.status & kStatusClass) {
+        set_error("orie_index_build: class id outside [0, %lld)", (long long)ix->C);
+        rc = ORIE_EDATA;
+    } else if (m.status & kStatusRows) {
+        set_error("orie_index_build: an image has more than 65535 rows in one file");
+        rc = ORIE_ELIMIT;
+    }
+    ix->resolved = true;
+    ix->resolved_rc = rc;
+    return rc;
 }
 
 }  // namespace orie
@@ -638,7 +729,7 @@ using namespace orie;
 extern "C" int orie_index_build(int64_t M, int64_t C, int T, int64_t num_weak, int64_t num_strong, int64_t num_labels,
                                 const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                                 const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
-                                const int64_t *l_off, const int32_t *l_cls, int seg_chunks, orie_event_t tp_ready,
+                                const int64_t *l_off, const int32_t *l_cls, const orie_tuning_t *tuning, orie_event_t tp_ready,
                                 orie_stream_t stream, orie_index_t **out) {
     if (!out) {
         set_error("orie_index_build: out is NULL");
@@ -658,6 +749,9 @@ extern "C" int orie_index_build(int64_t M, int64_t C, int T, int64_t num_weak, i
                   (long long)M, (long long)C);
         return ORIE_ELIMIT;
     }
+    orie_tuning_t tune;
+    memset(&tune, 0, sizeof(tune));
+    if (tuning) tune = *tuning;
     orie_index *ix = new orie_index();
     ix->M = M; ix->C = C; ix->T = T;
     ix->Dw = num_weak; ix->Ds = num_strong; ix->G = num_labels;
@@ -666,7 +760,16 @@ extern "C" int orie_index_build(int64_t M, int64_t C, int T, int64_t num_weak, i
     ix->ens_words = ceil_div(M + 1, 32);
     ix->cls_per_warp = 32 / T;
     ix->class_groups = ceil_div(C, ix->cls_per_warp);
-    int rc = build(ix, w_off, w_cls, w_conf, w_tp, s_off, s_cls, s_conf, s_tp, l_off, l_cls, seg_chunks, tp_ready, stream);
+    ix->walk_gmem = tune.walk_gmem;
+    ix->ap_mode = tune.ap_mode;
+    ix->walk_waves = tune.walk_waves;
+    int rc = ORIE_OK;
+    if (cudaEventCreateWithFlags(&ix->ready, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("orie_index_build: cannot create an event");
+        rc = ORIE_ECUDA;
+    }
+    if (rc == ORIE_OK)
+        rc = build(ix, w_off, w_cls, w_conf, w_tp, s_off, s_cls, s_conf, s_tp, l_off, l_cls, tune, tp_ready, stream);
     if (rc != ORIE_OK) {
         orie_index_destroy(ix);
         return rc;
@@ -678,7 +781,26 @@ extern "C" int orie_index_build(int64_t M, int64_t C, int T, int64_t num_weak, i
 extern "C" void orie_index_destroy(orie_index_t *ix) {
     if (!ix) return;
     for (int i = 0; i < ix->n_allocs; ++i) cudaFreeAsync(ix->allocs[i], ix->stream);
+    if (ix->ready) cudaEventDestroy(ix->ready);
     delete ix;
+}
+
+extern "C" int orie_index_status(const orie_index_t *ix) {
+    if (!ix) {
+        set_error("orie_index_status: index is NULL");
+        return ORIE_EINVAL;
+    }
+    ORIE_TRY(resolve(ix));
+    // the reward pass may have flagged a workspace that was too small for the event lists since the build
+    IndexMeta m;
+    ORIE_CUDA(cudaStreamSynchronize(ix->stream));
+    ORIE_CUDA(cudaMemcpy(&m, ix->meta, sizeof(m), cudaMemcpyDeviceToHost));
+    if (m.status & kStatusWorkspace) {
+        set_error("orie_reward: the workspace of an earlier call was too small for the event lists (%u events per target); "
+                  "size it with orie_reward_workspace_bytes or orie_reward_workspace_bound", m.Ev);
+        return ORIE_EWORKSPACE;
+    }
+    return ORIE_OK;
 }
 
 extern "C" int orie_index_info(const orie_index_t *ix, orie_index_info_t *info) {
@@ -686,6 +808,7 @@ extern "C" int orie_index_info(const orie_index_t *ix, orie_index_info_t *info) 
         set_error("orie_index_info: null argument");
         return ORIE_EINVAL;
     }
+    ORIE_TRY(resolve(ix));
     info->num_images = ix->M; info->num_classes = ix->C;
     info->num_thresholds = ix->T; info->seg_chunks = ix->seg_chunks;
     info->num_weak = ix->Dw; info->num_strong = ix->Ds; info->num_labels = ix->G;

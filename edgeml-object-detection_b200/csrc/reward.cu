@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "index.cuh"
 
@@ -167,21 +168,22 @@ ens_sample_kernel(int64_t nt, int64_t N, int64_t t0, int64_t M, int64_t words, u
 // ----------------------------------------------------------------------------
 struct WalkParams {
     int64_t M, nt, ntp, t0;
+    IndexMeta *meta;            // device-side sizes of the index (segments, events) and the sticky status word
+    int64_t S_cap;              // stride of bqoff rows (host-side upper bound of the segment count)
     int64_t ens_words;
     const uint32_t *ens_bits;   // [nt][ens_words]
     uint32_t *memb_global;      // [ntp / 32][ens_words * 32] membership tables in global memory (GMEM kernels)
     // stream
     const uint32_t *slot_img;
     const int32_t *seg_chunk0, *seg_nch;
-    int64_t S;
     int segs_per_block;
     uint32_t *tot;              // [S][ntp]
     // detection stream only
     const uint16_t *slot_tp;
     const uint32_t *seg_ev0;
     const uint2 *bq;            // per-batch query list (both detectors), ascending by slot
-    const uint32_t *bqoff;      // [nbatch][S+1]
-    int64_t Ev;
+    const uint32_t *bqoff;      // [nbatch][S_cap+1]
+    int64_t Ev;                 // capacity of one target's event list in the workspace (>= the index's event count)
     uint32_t *evcnt;            // [S][ntp]
     uint32_t *ev;               // [ntp][Ev] event records: rank inside the segment (16 bits) | TP mask << 16
     uint32_t *cb_w, *cb_s;
@@ -218,6 +220,15 @@ walk_kernel(const WalkParams p) {
     // batches in flight at any time stay L2-resident (a few dozen x 200 KB instead of one per resident block)
     const int64_t lb = GMEM ? blockIdx.y : blockIdx.x;   // local batch
     const int64_t yb = GMEM ? blockIdx.x : blockIdx.y;   // segment group
+    // the grid is sized from the host's upper bound of the segment count; the exact count lives on the device
+    const uint32_t status = p.meta->status;
+    const int64_t S = DETS ? p.meta->S : p.meta->SL;
+    if (status & (kStatusRows | kStatusClass | kStatusCounts)) return;       // the index build rejected its input
+    if (DETS && (int64_t)p.meta->Ev > p.Ev) {                                // event lists would not fit the workspace
+        if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicOr(&p.meta->status, kStatusWorkspace);
+        return;
+    }
+    if (yb * p.segs_per_block >= S) return;
     const int64_t tl = lb * 32 + lane;             // local target of this lane
     Transposer transpose;
     transpose.init(lane);
@@ -233,7 +244,7 @@ walk_kernel(const WalkParams p) {
     }
     const int64_t gb = (p.t0 >> 5) + lb;           // global batch (query lists are per global batch)
     const int64_t sbeg = yb * p.segs_per_block;
-    const int64_t send = min(sbeg + p.segs_per_block, p.S);
+    const int64_t send = min(sbeg + p.segs_per_block, S);
     for (int64_t s = sbeg + warp; s < send; s += kWarps) {
         const int64_t ch0 = p.seg_chunk0[s];
         const int nch = p.seg_nch[s];
@@ -243,7 +254,7 @@ walk_kernel(const WalkParams p) {
         uint32_t *evout = nullptr;
         if (DETS) {
             evout = p.ev + tl * p.Ev + p.seg_ev0[s];
-            const uint32_t *o = p.bqoff + gb * (p.S + 1) + s;
+            const uint32_t *o = p.bqoff + gb * (p.S_cap + 1) + s;
             qi = o[0]; q_end = o[1];
             if (qi < q_end) nq = p.bq[qi];
         }
@@ -298,8 +309,11 @@ struct ApParams {
     int64_t M, C, nt, ntp, t0;
     int T, cls_per_warp;
     int64_t class_groups;
-    int64_t S, SL, Ev;
+    int64_t Ev;                 // stride of the per-target event lists in the workspace
+    const IndexMeta *meta;
     const int32_t *cls_seg0, *seg_chunk0, *lcls_seg0, *cls_order;
+    const uint16_t *act_cls;    // [M][C] classes with an own detection, per image
+    const uint32_t *nact;       // [M]
     const uint32_t *seg_ev0;
     const uint32_t *tot, *evcnt, *totL;
     const uint32_t *ev;
@@ -308,6 +322,7 @@ struct ApParams {
     const uint16_t *own_w_cs, *own_s_cs, *own_w_m, *own_s_m;
     const uint32_t *own_w_q, *own_s_q, *cb_w, *cb_s;
     double *partial;    // [ntp][class_groups][3]
+    uint32_t *depths;   // measurement only (orie_reward_depths): [nt][C][T][2] loop trips of the sweep / its tail
 };
 
 // Reverse-sweep state of one (class, threshold, variant) AP integral; oracle/event_model.py:_Var
@@ -419,20 +434,33 @@ struct OwnCursor {
 
 constexpr int kApThreads = 128;
 
+// One warp per (target, group of 32/T classes); lane = (class slot, IoU threshold).
+//
 // FULL = false (normal operation): only the DIFFERENCE of the two variants' integrals is needed, so
-//  * a class in which the target has no detection from either detector is skipped (identical integrals);
+//  * a class in which the target has no detection from either detector is skipped (identical integrals): the warp's
+//    classes come from the image's list of classes WITH an own detection (act_cls, built with the index), so the
+//    lanes of the warps that do run are all busy and the other warps of the target leave at once;
 //  * the sweep of a (class, threshold) stops as soon as the variants can no longer differ: once every own
 //    detection lies behind (lower confidence), both variants see the same ranks, the same count of remaining true
 //    positives and the same grid pointer; from then on they take the max with the same ratios, so when their
 //    envelope values meet they stay equal and every later (higher-confidence) term cancels exactly.
 //    The sums written are then partial (common part omitted in both).
-// FULL = true (detail requested): both integrals are completed, the sums are the true AP sums.
-template <bool FULL>
+// FULL = true (detail requested): every class, both integrals completed, the sums are the true AP sums.
+//
+// The number of ground-truth classes (the mean's denominator, lib/metrics.py:104-107) is counted separately, lane =
+// class, by the first ceil(C / 32) warps of the target.  The number of member true positives of a class at every
+// threshold (K, where the reverse sweep starts) is counted by the whole warp: 32 event records per step, one ballot
+// per threshold.
+// MODE bits (orie_tuning_t::ap_mode selects among the instantiations): 1 = member true positives counted by the whole
+// warp (32 records per step, one ballot per threshold) instead of per lane; 2 = the warp's classes come from the
+// image's active-class list instead of fixed cls_order groups.
+template <bool FULL, int MODE, bool DEPTHS = false>
 __global__ void __launch_bounds__(kApThreads, 8)
 ap_kernel(const ApParams p, const Grid101 grid) {
     __shared__ double cw[102];
     __shared__ double cwx[102];
     __shared__ uint32_t ge[5];
+    if (p.meta->status) return;                 // uniform: rejected input or a workspace flagged too small by the walk
     for (int i = threadIdx.x; i < 102; i += kApThreads) { cw[i] = grid.cw[i]; cwx[i] = grid.cwx[i]; }
     if (threadIdx.x < 5) ge[threadIdx.x] = grid.ge[threadIdx.x];
     __syncthreads();
@@ -440,37 +468,87 @@ ap_kernel(const ApParams p, const Grid101 grid) {
     const int64_t item = (int64_t)blockIdx.x * (kApThreads / 32) + (threadIdx.x >> 5);
     if (item >= p.nt * p.class_groups) return;
     const int64_t tl = item / p.class_groups, grp = item % p.class_groups;
-    const int slot = lane / p.T, t = lane % p.T;
-    const int64_t ci = grp * p.cls_per_warp + slot;
-    const bool active = slot < p.cls_per_warp && ci < p.C;
     const int64_t j = p.t0 + tl;
+    const uint32_t *tot = p.tot + tl, *evcnt = p.evcnt + tl;
+    const uint32_t *ev = p.ev + tl * p.Ev;
 
-    double ap_w = 0.0, ap_s = 0.0, has_gt = 0.0;
-    if (active) {
-        const int c = p.cls_order[ci];          // classes of similar size share a warp
-        uint32_t n_l = p.gtcnt[j * p.C + c];
-        for (int ls = p.lcls_seg0[c]; ls < p.lcls_seg0[c + 1]; ++ls) n_l += p.totL[(int64_t)ls * p.ntp + tl];
-        const uint16_t *wcs = p.own_w_cs + j * (p.C + 1) + c, *scs = p.own_s_cs + j * (p.C + 1) + c;
-        const int wa = wcs[0], wb = wcs[1], sa = scs[0], sb = scs[1];
+    // ---- classes with ground truth in E + {target}: lane = class
+    double has_gt = 0.0;
+    if (grp * 32 < p.C) {
+        const int64_t c = grp * 32 + lane;
+        bool has = false;
+        if (c < p.C) {
+            uint32_t n_l = p.gtcnt[j * p.C + c];
+            for (int ls = p.lcls_seg0[c]; ls < p.lcls_seg0[c + 1] && n_l == 0; ++ls) n_l += p.totL[(int64_t)ls * p.ntp + tl];
+            has = n_l > 0;
+        }
+        has_gt = (double)__popc(__ballot_sync(kFull, has));
+    }
+
+    // ---- AP integrals of this warp's classes
+    constexpr bool kActList = !FULL && (MODE & 2);
+    const int64_t nact = kActList ? (int64_t)p.nact[j] : p.C;
+    const int64_t first = grp * p.cls_per_warp;
+    double ap_w = 0.0, ap_s = 0.0;
+    if (first < nact) {
+        const int slot = lane / p.T, t = lane % p.T;
+        const int64_t ci = first + slot;
+        const bool active = slot < p.cls_per_warp && ci < nact;
+        int c = 0, wa = 0, wb = 0, sa = 0, sb = 0;
+        uint32_t n_l = 0;
+        if (active) {
+            c = kActList ? (int)p.act_cls[j * p.C + ci] : p.cls_order[ci];     // classes of similar size share a warp
+            n_l = p.gtcnt[j * p.C + c];
+            for (int ls = p.lcls_seg0[c]; ls < p.lcls_seg0[c + 1]; ++ls) n_l += p.totL[(int64_t)ls * p.ntp + tl];
+            const uint16_t *wcs = p.own_w_cs + j * (p.C + 1) + c, *scs = p.own_s_cs + j * (p.C + 1) + c;
+            wa = wcs[0]; wb = wcs[1]; sa = scs[0]; sb = scs[1];
+        }
         // the target has no detection of this class from either detector: both variants are the same integral
         const bool same = (wb == wa) && (sb == sa);
-        if (n_l > 0 && t == 0) has_gt = 1.0;
-        if (n_l > 0 && (FULL || !same)) {
-            const int s0 = p.cls_seg0[c], s1 = p.cls_seg0[c + 1];
-            const uint32_t *ev = p.ev + tl * p.Ev;
-            const uint32_t *tot = p.tot + tl, *evcnt = p.evcnt + tl;
-            uint32_t n_ens = 0, K_ens = 0;
+        const bool need = active && n_l > 0 && (FULL || !same);
+        // members of the class (n_ens) and member true positives at this lane's threshold (K_ens), by the whole warp
+        uint32_t n_ens = 0, K_ens = 0;
+        const int nslots = (int)min((int64_t)p.cls_per_warp, nact - first);
+        if (!(MODE & 1)) {
+            if (need) {
+                const int s0 = p.cls_seg0[c], s1 = p.cls_seg0[c + 1];
+                for (int s = s0; s < s1; ++s) {
+                    n_ens += tot[(int64_t)s * p.ntp];
+                    const uint32_t *e = ev + p.seg_ev0[s];
+                    const int ne = (int)evcnt[(int64_t)s * p.ntp];
+                    int i = 0;
+                    for (; i + 4 <= ne; i += 4) {           // four independent loads in flight
+                        const uint32_t a = e[i], b = e[i + 1], c2 = e[i + 2], d = e[i + 3];
+                        K_ens += ((a >> (16 + t)) & 1u) + ((b >> (16 + t)) & 1u) + ((c2 >> (16 + t)) & 1u) + ((d >> (16 + t)) & 1u);
+                    }
+                    for (; i < ne; ++i) K_ens += (e[i] >> (16 + t)) & 1u;
+                }
+            }
+        } else
+        for (int sl = 0; sl < nslots; ++sl) {
+            const int src = sl * p.T;
+            if (!__shfl_sync(kFull, (int)need, src)) continue;             // uniform
+            const int cc = __shfl_sync(kFull, c, src);
+            const int s0 = p.cls_seg0[cc], s1 = p.cls_seg0[cc + 1];
+            uint32_t acc_n = 0, acc_k = 0;
+            for (int s = s0 + lane; s < s1; s += 32) acc_n += tot[(int64_t)s * p.ntp];
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) acc_n += __shfl_xor_sync(kFull, acc_n, d);
             for (int s = s0; s < s1; ++s) {
-                n_ens += tot[(int64_t)s * p.ntp];
                 const uint32_t *e = ev + p.seg_ev0[s];
                 const int ne = (int)evcnt[(int64_t)s * p.ntp];
-                int i = 0;
-                for (; i + 4 <= ne; i += 4) {           // four independent loads in flight
-                    const uint32_t a = e[i], b = e[i + 1], c2 = e[i + 2], d = e[i + 3];
-                    K_ens += ((a >> (16 + t)) & 1u) + ((b >> (16 + t)) & 1u) + ((c2 >> (16 + t)) & 1u) + ((d >> (16 + t)) & 1u);
+                for (int i0 = 0; i0 < ne; i0 += 32) {
+                    const uint32_t rec = i0 + lane < ne ? e[i0 + lane] : 0u;
+                    for (int tt = 0; tt < p.T; ++tt) {
+                        const unsigned b = __ballot_sync(kFull, (rec >> (16 + tt)) & 1u);
+                        if (tt == t) acc_k += __popc(b);
+                    }
                 }
-                for (; i < ne; ++i) K_ens += (e[i] >> (16 + t)) & 1u;
             }
+            if (slot == sl) { n_ens = acc_n; K_ens = acc_k; }
+        }
+        if (need) {
+            const int s0 = p.cls_seg0[c], s1 = p.cls_seg0[c + 1];
             const uint32_t *wq = p.own_w_q + p.w_off[j], *wcb = p.cb_w + p.w_off[j];
             const uint32_t *sq = p.own_s_q + p.s_off[j], *scb = p.cb_s + p.s_off[j];
             const uint16_t *wm = p.own_w_m + p.w_off[j], *sm = p.own_s_m + p.s_off[j];
@@ -491,7 +569,9 @@ ap_kernel(const ApParams p, const Grid101 grid) {
                 uint32_t base = n_ens, slot0 = 0;
                 const uint32_t *e = ev;
                 bool tail = false;
+                uint32_t trips_main = 0, trips_tail = 0;
                 for (;;) {
+                    if (DEPTHS) ++trips_main;
                     if (!FULL && !ow.valid && !os.valid) {
                         // every own detection lies behind: no true positive left in front of either variant -> nothing
                         // can change any more; both alive with the same count and grid pointer -> continue in the tail loop
@@ -527,6 +607,7 @@ ap_kernel(const ApParams p, const Grid101 grid) {
                 // and the integrals differ, and they stop differing when the envelopes meet.  One ratio per event
                 // serves both variants and events that are not true positives at this threshold cost a load and a test.
                 while (tail && vw.E != vs.E) {
+                    if (DEPTHS) ++trips_tail;
                     if (i < 0) {
                         if (s == s0) break;
                         --s;
@@ -552,16 +633,19 @@ ap_kernel(const ApParams p, const Grid101 grid) {
                         vw.g = gl - 1;
                     }
                 }
+                if (DEPTHS) {
+                    uint32_t *d = p.depths + ((tl * p.C + c) * p.T + t) * 2;
+                    d[0] = trips_main; d[1] = trips_tail;
+                }
             }
             ap_w = vw.dead ? 0.0 : vw.ap;
             ap_s = same ? ap_w : (vs.dead ? 0.0 : vs.ap);
         }
-    }
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        ap_w = __dadd_rn(ap_w, __shfl_xor_sync(kFull, ap_w, d));
-        ap_s = __dadd_rn(ap_s, __shfl_xor_sync(kFull, ap_s, d));
-        has_gt += __shfl_xor_sync(kFull, has_gt, d);
+        for (int d = 16; d >= 1; d >>= 1) {
+            ap_w = __dadd_rn(ap_w, __shfl_xor_sync(kFull, ap_w, d));
+            ap_s = __dadd_rn(ap_s, __shfl_xor_sync(kFull, ap_s, d));
+        }
     }
     if (lane == 0) {
         double *out = p.partial + (tl * p.class_groups + grp) * 3;
@@ -572,49 +656,97 @@ ap_kernel(const ApParams p, const Grid101 grid) {
 // ----------------------------------------------------------------------------
 // K3
 // ----------------------------------------------------------------------------
+// (N + 1) * (mean strong AP - mean weak AP) from the sums; no ground-truth class: upstream's mean over an empty AP
+// table is NaN, stored as 0 (reward.py:50,86)
+__device__ __forceinline__ double reward_from_sums(double sw, double ss, double nc, int T, int64_t N) {
+    if (!(nc > 0.0)) return 0.0;
+    const double cnt = nc * (double)T;
+    return __dmul_rn(__dsub_rn(__ddiv_rn(ss, cnt), __ddiv_rn(sw, cnt)), (double)(N + 1));
+}
+
 __global__ void finalize_kernel(const double *__restrict__ partial, int64_t nt, int64_t groups, int T, int64_t N,
-                                double *__restrict__ reward, double *__restrict__ detail) {
+                                const IndexMeta *__restrict__ meta, double *__restrict__ reward, double *__restrict__ detail) {
     const int64_t tl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tl >= nt) return;
     double sw = 0.0, ss = 0.0, nc = 0.0;
+    if (meta->status) {                         // nothing was computed: make that impossible to miss
+        sw = ss = nc = __longlong_as_double(0x7ff8000000000000ll);
+        if (reward) reward[tl] = sw;
+        if (detail) { detail[tl * 3] = sw; detail[tl * 3 + 1] = ss; detail[tl * 3 + 2] = nc; }
+        return;
+    }
     for (int64_t g = 0; g < groups; ++g) {
         const double *q = partial + (tl * groups + g) * 3;
         sw = __dadd_rn(sw, q[0]);
         ss = __dadd_rn(ss, q[1]);
         nc += q[2];
     }
-    double r = 0.0;
-    if (nc > 0.0) {
-        const double cnt = nc * (double)T;
-        r = __dmul_rn(__dsub_rn(__ddiv_rn(ss, cnt), __ddiv_rn(sw, cnt)), (double)(N + 1));
-    }
-    if (reward) reward[tl] = r;   // nc == 0: upstream's mean over an empty AP table is NaN, stored as 0 (reward.py:86)
+    if (reward) reward[tl] = reward_from_sums(sw, ss, nc, T, N);
     if (detail) { detail[tl * 3] = sw; detail[tl * 3 + 1] = ss; detail[tl * 3 + 2] = nc; }
+}
+
+// rewards from (reduced) per-target sums: the last step of a class-sharded multi-GPU run, after the all-reduce
+__global__ void rewards_from_sums_kernel(const double *__restrict__ sums, int64_t nt, int T, int64_t N, double *__restrict__ reward) {
+    const int64_t tl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tl >= nt) return;
+    reward[tl] = reward_from_sums(sums[tl * 3], sums[tl * 3 + 1], sums[tl * 3 + 2], T, N);
 }
 
 // ----------------------------------------------------------------------------
 // workspace
 // ----------------------------------------------------------------------------
+// The per-segment tables are sized with the host-side segment capacities; the per-target event lists come last and take
+// whatever the caller's workspace has left (at least the index's event count, checked on the host once the exact
+// count is known, on the device otherwise).
 struct WsLayout {
-    size_t tot, evcnt, totL, ev, cb_w, cb_s, partial, memb, total;
+    size_t tot, evcnt, totL, cb_w, cb_s, partial, memb, ev, fixed;
 };
+
+static bool walk_in_gmem(const orie_index *ix) {
+    // beyond 112 KB a shared-memory table would allow only one 1024-thread block per SM; the L1/L2-served global
+    // table with six 256-thread blocks per SM is measurably faster there (profiles/: 157 vs 168 ms at M = 50 000)
+    return (size_t)ix->ens_words * 32 * 4 > 112 * 1024 || ix->walk_gmem != 0;
+}
 
 static WsLayout ws_layout(const orie_index *ix, int64_t nt) {
     const int64_t ntp = round_up(nt, 32);
     WsLayout L;
     size_t o = 0;
     auto take = [&](int64_t bytes) { size_t at = o; o += (size_t)round_up(bytes > 0 ? bytes : 1, 256); return at; };
-    L.tot = take(ix->S * ntp * 4);
-    L.evcnt = take(ix->S * ntp * 4);
-    L.totL = take(ix->SL * ntp * 4);
-    L.ev = take(ntp * ix->Ev * 4);
+    L.tot = take(ix->S_cap * ntp * 4);
+    L.evcnt = take(ix->S_cap * ntp * 4);
+    L.totL = take(ix->SL_cap * ntp * 4);
     L.cb_w = take(ix->Dw * 4);
     L.cb_s = take(ix->Ds * 4);
     L.partial = take(ntp * ix->class_groups * 3 * 8);
     // membership tables in global memory, only when they exceed shared memory (or when forced for tests)
-    L.memb = take(((size_t)ix->ens_words * 32 * 4 > 112 * 1024 || getenv("ORIE_WALK_GMEM")) ? (ntp / 32) * ix->ens_words * 32 * 4 : 0);
-    L.total = o;
+    L.memb = take(walk_in_gmem(ix) ? (ntp / 32) * ix->ens_words * 32 * 4 : 0);
+    L.ev = o;
+    L.fixed = o;
     return L;
+}
+
+static size_t ws_total(const orie_index *ix, int64_t nt, int64_t events) {
+    return ws_layout(ix, nt).fixed + (size_t)round_up(round_up(nt, 32) * std::max<int64_t>(events, 1) * 4, 256);
+}
+
+// one-time (per device) opt-in of the walk kernels to the shared memory their membership table may need
+static int walk_attributes() {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    ORIE_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 0 || dev >= 64 || done[dev]) return ORIE_OK;
+    const int smem = 112 * 1024;
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    done[dev] = true;
+    return ORIE_OK;
 }
 
 }  // namespace orie
@@ -623,7 +755,13 @@ using namespace orie;
 
 extern "C" size_t orie_reward_workspace_bytes(const orie_index_t *ix, int64_t nt) {
     if (!ix || nt < 0) return 0;
-    return ws_layout(ix, nt).total;
+    if (resolve(ix) != ORIE_OK) return 0;
+    return ws_total(ix, nt, ix->Ev);
+}
+
+extern "C" size_t orie_reward_workspace_bound(const orie_index_t *ix, int64_t nt) {
+    if (!ix || nt < 0) return 0;
+    return ws_total(ix, nt, ix->resolved ? ix->Ev : ix->Ev_cap);
 }
 
 static int check_range(const orie_index *ix, int64_t t0, int64_t nt, const char *who) {
@@ -676,8 +814,6 @@ extern "C" int orie_ensemble_sample(const orie_index_t *ix, int64_t t0, int64_t 
 
 template <bool DETS, int THREADS, bool GMEM>
 static int launch_walk_t(dim3 grid, size_t smem, cudaStream_t stream, const WalkParams &p) {
-    if (!GMEM)
-        ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<DETS, THREADS, GMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     walk_kernel<DETS, THREADS, GMEM><<<grid, THREADS, GMEM ? 0 : smem, stream>>>(p);
     return ORIE_OK;
 }
@@ -689,36 +825,65 @@ static int launch_walk(dim3 grid, int threads, size_t smem, bool gmem, cudaStrea
     return launch_walk_t<DETS, 1024, false>(grid, smem, stream, p);
 }
 
+// np.linspace(0, 1, 101) and the cumulative trapezoid weights of np.trapz over it, bit for bit
+static const Grid101 &grid101() {
+    static const Grid101 g = [] {
+        Grid101 grid;
+        double x[101], w[101];
+        for (int i = 0; i <= 100; ++i) { x[i] = (double)i * 0.01; w[i] = 0.0; }   // == np.linspace(0, 1, 101) bit for bit
+        x[100] = 1.0;
+        for (int i = 0; i < 100; ++i) {
+            const double d = x[i + 1] - x[i];          // np.diff
+            w[i] += d / 2; w[i + 1] += d / 2;
+        }
+        grid.cw[0] = grid.cwx[0] = 0.0;
+        for (int i = 0; i <= 100; ++i) {
+            grid.cw[i + 1] = grid.cw[i] + w[i];
+            grid.cwx[i + 1] = grid.cwx[i] + w[i] * x[i];
+        }
+        for (int k = 0; k < 4; ++k) grid.ge[k] = 0;
+        for (int i = 0; i <= 100; ++i)
+            if (x[i] >= (double)i / 100.0) grid.ge[i >> 5] |= 1u << (i & 31);
+        grid.ge[4] = (grid.ge[0] == 0xffffffffu && grid.ge[1] == 0xffffffffu && grid.ge[2] == 0xffffffffu &&
+                      grid.ge[3] == 0x1fu) ? 1u : 0u;
+        return grid;
+    }();
+    return g;
+}
+
 static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
                       void *workspace, size_t workspace_bytes, double *reward, double *detail, bool full,
-                      cudaStream_t stream, cudaEvent_t *marks /* 5 events or NULL */) {
+                      cudaStream_t stream, cudaEvent_t *marks /* 5 events or NULL */, uint32_t *depths = nullptr) {
     ORIE_TRY(check_range(ix, t0, nt, "orie_reward"));
     if (!ens_bits || (!reward && !detail) || !workspace || N < 0) {
         set_error("orie_reward: null buffer or negative N");
         return ORIE_EINVAL;
     }
     if (nt == 0) return ORIE_OK;
+    if (ix->resolved && ix->resolved_rc != ORIE_OK) return resolve(ix);
     const WsLayout L = ws_layout(ix, nt);
-    if (workspace_bytes < L.total) {
-        set_error("orie_reward: workspace has %zu bytes, %zu needed for %lld targets", workspace_bytes, L.total, (long long)nt);
+    const int64_t ntp = round_up(nt, 32);
+    // capacity of one target's event list: what the workspace has left after the fixed tables
+    const int64_t ev_stride = workspace_bytes > L.fixed ? (int64_t)((workspace_bytes - L.fixed) / ((size_t)ntp * 4)) : 0;
+    if (ev_stride < 1 || (ix->resolved && ev_stride < ix->Ev)) {
+        set_error("orie_reward: workspace has %zu bytes, %zu needed for %lld targets", workspace_bytes,
+                  ws_total(ix, nt, ix->resolved ? ix->Ev : 1), (long long)nt);
         return ORIE_EWORKSPACE;
     }
     if ((uintptr_t)workspace & 255) {
         set_error("orie_reward: workspace must be 256-byte aligned");
         return ORIE_EINVAL;
     }
+    ORIE_TRY(walk_attributes());
     char *ws = (char *)workspace;
-    const int64_t ntp = round_up(nt, 32);
     const size_t smem = (size_t)ix->ens_words * 32 * 4;
-    const char *force_gmem = getenv("ORIE_WALK_GMEM");               // developer / test knob
-    // beyond 112 KB a shared-memory table would allow only one 1024-thread block per SM; the L1/L2-served global
-    // table with six 256-thread blocks per SM is measurably faster there (profiles/: 157 vs 168 ms at M = 50 000)
-    const bool gmem = smem > 112 * 1024 || (force_gmem && atoi(force_gmem) != 0);
+    const bool gmem = walk_in_gmem(ix);
     static_assert(sizeof(WalkParams) < 4000 && sizeof(ApParams) + sizeof(Grid101) < 4000, "kernel parameter space");
 
     WalkParams wp;
     memset(&wp, 0, sizeof(wp));
     wp.M = ix->M; wp.nt = nt; wp.ntp = ntp; wp.t0 = t0;
+    wp.meta = ix->meta; wp.S_cap = ix->S_cap;
     wp.ens_words = ix->ens_words; wp.ens_bits = ens_bits;
     const int64_t nb = ntp / 32;
     const int walk_threads = gmem ? 256 : smem <= 56 * 1024 ? 256 : 512;   // keep the SM full of warps
@@ -726,8 +891,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         // enough blocks for two full waves of resident blocks (2048 threads per SM) when the data allows,
         // at least one segment per warp
         const int64_t resident = 148 * (kWalkResident / walk_threads > 0 ? kWalkResident / walk_threads : 1);
-        const char *tune = getenv("ORIE_WALK_WAVES");          // developer knob (profiles/tune.py)
-        const double waves = tune ? atof(tune) : 2.0;
+        const double waves = ix->walk_waves > 0.0 ? ix->walk_waves : 2.0;
         int64_t want_y = (int64_t)((waves * (double)resident + (double)nb - 1.0) / (double)nb);
         if (gmem) want_y = std::max<int64_t>(want_y, 32);     // many blocks per batch: few tables in flight
         int64_t spb = ceil_div(S, want_y > 0 ? want_y : 1);
@@ -740,6 +904,8 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
                   65535 * 32, (long long)nt);
         return ORIE_ELIMIT;
     }
+    // launch grids come from the exact segment counts when the host already knows them, else from their upper bounds
+    const int64_t S_grid = ix->resolved ? ix->S : ix->S_cap, SL_grid = ix->resolved ? ix->SL : ix->SL_cap;
     if (marks) ORIE_CUDA(cudaEventRecord(marks[0], stream));
     if (gmem) {
         wp.memb_global = (uint32_t *)(ws + L.memb);
@@ -748,12 +914,12 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         ORIE_LAUNCH_CHECK();
     }
     // labels
-    if (ix->SL > 0) {
+    if (SL_grid > 0) {
         WalkParams lp = wp;
         lp.slot_img = ix->lab_slot_img; lp.seg_chunk0 = ix->lseg_chunk0; lp.seg_nch = ix->lseg_nch;
-        lp.S = ix->SL; lp.segs_per_block = segs_per_block(ix->SL);
+        lp.segs_per_block = segs_per_block(SL_grid);
         lp.tot = (uint32_t *)(ws + L.totL);
-        const unsigned ny = (unsigned)ceil_div(ix->SL, lp.segs_per_block);
+        const unsigned ny = (unsigned)ceil_div(SL_grid, lp.segs_per_block);
         dim3 grid = gmem ? dim3(ny, (unsigned)nb) : dim3((unsigned)nb, ny);
         ORIE_TRY(launch_walk<false>(grid, walk_threads, smem, gmem, stream, lp));
         ORIE_LAUNCH_CHECK();
@@ -762,16 +928,16 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     // detections
     {
         wp.slot_img = ix->slot_img; wp.seg_chunk0 = ix->seg_chunk0; wp.seg_nch = ix->seg_nch;
-        wp.S = ix->S; wp.segs_per_block = segs_per_block(ix->S);
+        wp.segs_per_block = segs_per_block(S_grid);
         wp.tot = (uint32_t *)(ws + L.tot);
         wp.slot_tp = ix->slot_tp; wp.seg_ev0 = ix->seg_ev0;
         wp.bq = ix->bq; wp.bqoff = ix->bqoff;
-        wp.Ev = ix->Ev;
+        wp.Ev = ev_stride;
         wp.evcnt = (uint32_t *)(ws + L.evcnt);
         wp.ev = (uint32_t *)(ws + L.ev);
         wp.cb_w = (uint32_t *)(ws + L.cb_w);
         wp.cb_s = (uint32_t *)(ws + L.cb_s);
-        const unsigned ny = (unsigned)ceil_div(ix->S, wp.segs_per_block);
+        const unsigned ny = (unsigned)ceil_div(S_grid, wp.segs_per_block);
         dim3 grid = gmem ? dim3(ny, (unsigned)nb) : dim3((unsigned)nb, ny);
         ORIE_TRY(launch_walk<true>(grid, walk_threads, smem, gmem, stream, wp));
         ORIE_LAUNCH_CHECK();
@@ -782,8 +948,9 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     memset(&ap, 0, sizeof(ap));
     ap.M = ix->M; ap.C = ix->C; ap.nt = nt; ap.ntp = ntp; ap.t0 = t0;
     ap.T = ix->T; ap.cls_per_warp = ix->cls_per_warp; ap.class_groups = ix->class_groups;
-    ap.S = ix->S; ap.SL = ix->SL; ap.Ev = ix->Ev;
+    ap.Ev = ev_stride; ap.meta = ix->meta;
     ap.cls_order = ix->cls_order; ap.cls_seg0 = ix->cls_seg0; ap.seg_chunk0 = ix->seg_chunk0; ap.lcls_seg0 = ix->lcls_seg0; ap.seg_ev0 = ix->seg_ev0;
+    ap.act_cls = ix->act_cls; ap.nact = ix->nact;
     ap.tot = (const uint32_t *)(ws + L.tot); ap.evcnt = (const uint32_t *)(ws + L.evcnt);
     ap.totL = (const uint32_t *)(ws + L.totL); ap.ev = (const uint32_t *)(ws + L.ev);
     ap.gtcnt = ix->gtcnt; ap.w_off = ix->w_off; ap.s_off = ix->s_off;
@@ -791,32 +958,17 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     ap.own_w_q = ix->own_w_q; ap.own_s_q = ix->own_s_q;
     ap.cb_w = (const uint32_t *)(ws + L.cb_w); ap.cb_s = (const uint32_t *)(ws + L.cb_s);
     ap.partial = (double *)(ws + L.partial);
-    Grid101 grid101;
-    {
-        double x[101], w[101];
-        for (int g = 0; g <= 100; ++g) { x[g] = (double)g * 0.01; w[g] = 0.0; }   // == np.linspace(0, 1, 101) bit for bit
-        x[100] = 1.0;
-        for (int g = 0; g < 100; ++g) {
-            const double d = x[g + 1] - x[g];          // np.diff
-            w[g] += d / 2; w[g + 1] += d / 2;
-        }
-        grid101.cw[0] = grid101.cwx[0] = 0.0;
-        for (int g = 0; g <= 100; ++g) {
-            grid101.cw[g + 1] = grid101.cw[g] + w[g];
-            grid101.cwx[g + 1] = grid101.cwx[g] + w[g] * x[g];
-        }
-        for (int k = 0; k < 4; ++k) grid101.ge[k] = 0;
-        for (int g = 0; g <= 100; ++g)
-            if (x[g] >= (double)g / 100.0) grid101.ge[g >> 5] |= 1u << (g & 31);
-        grid101.ge[4] = (grid101.ge[0] == 0xffffffffu && grid101.ge[1] == 0xffffffffu && grid101.ge[2] == 0xffffffffu &&
-                         grid101.ge[3] == 0x1fu) ? 1u : 0u;
-    }
+    ap.depths = depths;
     const int64_t items = nt * ix->class_groups;
-    if (full) ap_kernel<true><<<(unsigned)ceil_div(items, kApThreads / 32), kApThreads, 0, stream>>>(ap, grid101);
-    else ap_kernel<false><<<(unsigned)ceil_div(items, kApThreads / 32), kApThreads, 0, stream>>>(ap, grid101);
+    const unsigned ap_grid = (unsigned)ceil_div(items, kApThreads / 32);
+    if (depths) ap_kernel<false, 0, true><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());
+    else if (full) ap_kernel<true, 0><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());
+    else if (ix->ap_mode == 1) ap_kernel<false, 0><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());   // fixed cls_order groups
+    else if (ix->ap_mode == 3) ap_kernel<false, 3><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());
+    else ap_kernel<false, 2><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());      // default: depth-ordered active classes
     ORIE_LAUNCH_CHECK();
     if (marks) ORIE_CUDA(cudaEventRecord(marks[3], stream));
-    finalize_kernel<<<(unsigned)ceil_div(nt, 128), 128, 0, stream>>>(ap.partial, nt, ix->class_groups, ix->T, N, reward, detail);
+    finalize_kernel<<<(unsigned)ceil_div(nt, 128), 128, 0, stream>>>(ap.partial, nt, ix->class_groups, ix->T, N, ix->meta, reward, detail);
     ORIE_LAUNCH_CHECK();
     if (marks) ORIE_CUDA(cudaEventRecord(marks[4], stream));
     return ORIE_OK;
@@ -834,6 +986,26 @@ extern "C" int orie_reward_sums(const orie_index_t *ix, int64_t t0, int64_t nt, 
         return ORIE_EINVAL;
     }
     return run_reward(ix, t0, nt, ens_bits, N, workspace, workspace_bytes, nullptr, sums, full != 0, stream, nullptr);
+}
+
+extern "C" int orie_reward_depths(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
+                                  void *workspace, size_t workspace_bytes, double *reward, uint32_t *depths, orie_stream_t stream) {
+    if (!depths || !reward) {
+        set_error("orie_reward_depths: null buffer");
+        return ORIE_EINVAL;
+    }
+    return run_reward(ix, t0, nt, ens_bits, N, workspace, workspace_bytes, reward, nullptr, false, stream, nullptr, depths);
+}
+
+extern "C" int orie_rewards_from_sums(const double *sums, int64_t nt, int T, int64_t N, double *reward, orie_stream_t stream) {
+    if (!sums || !reward || nt < 0 || T < 1 || N < 0) {
+        set_error("orie_rewards_from_sums: null buffer or bad size");
+        return ORIE_EINVAL;
+    }
+    if (nt == 0) return ORIE_OK;
+    rewards_from_sums_kernel<<<(unsigned)ceil_div(nt, 256), 256, 0, stream>>>(sums, nt, T, N, reward);
+    ORIE_LAUNCH_CHECK();
+    return ORIE_OK;
 }
 
 extern "C" int orie_reward_profile(const orie_index_t *ix, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,

@@ -274,8 +274,6 @@ int sort_max_blocks(int *out) {
     ORIE_TRY(coop_max_blocks(coop_radix_kernel<true>, kSortThreads, 0, &a));
     ORIE_TRY(coop_max_blocks(coop_radix_kernel<false>, kSortThreads, 0, &b));
     *out = a < b ? a : b;
-    const char *cap = getenv("ORIE_SORT_MAX_BLOCKS");    // test knob: few CTAs force the multi-tile path on small inputs
-    if (cap && atoi(cap) > 0 && atoi(cap) < *out) *out = atoi(cap);
     return ORIE_OK;
 }
 

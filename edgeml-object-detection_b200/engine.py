@@ -95,7 +95,16 @@ def pick_shard(num_images: int, shard: str = "auto") -> str:
 
 
 def rewards_from_sums(sums, T: int, n_used: int):
-    """(mean strong AP - mean weak AP) * (N + 1) from per-target sums (torch or numpy), NaN -> 0 (reward.py:50,86)."""
+    """(mean strong AP - mean weak AP) * (N + 1) from per-target sums, NaN -> 0 (reward.py:50,86).  CUDA tensors go
+    through one kernel of the library (``orie_rewards_from_sums``) on the current stream; numpy arrays and CPU tensors
+    (host-side checks, the gloo tests) are evaluated with the same formula on the host."""
+    if torch.is_tensor(sums) and sums.is_cuda:
+        sums = sums.contiguous()
+        out = torch.empty(sums.shape[0], dtype=torch.float64, device=sums.device)
+        with torch.cuda.device(sums.device):
+            _lib.check(_lib.load().orie_rewards_from_sums(_ptr(sums), sums.shape[0], int(T), int(n_used), _ptr(out),
+                                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
     sw, ss, nc = sums[:, 0], sums[:, 1], sums[:, 2]
     cnt = nc * T
     safe = cnt.clamp(min=1) if torch.is_tensor(cnt) else np.maximum(cnt, 1)
@@ -141,11 +150,14 @@ class DevicePacked:
 
 
 class Engine:
-    def __init__(self, packed, iouv=IOU_05, device=None, seg_chunks: int = 0, stream=None, index: bool = True):
+    def __init__(self, packed, iouv=IOU_05, device=None, seg_chunks: int = 0, stream=None, index: bool = True,
+                 tuning: dict | None = None):
         """``packed``: ``Packed`` (host numpy), ``HostPacked`` (pinned) or
         ``DevicePacked`` (already in HBM).  Uploads if needed, then runs TP
         matching for both detectors and builds the dataset index (``index=False``: matching only — all
-        that ``tp_flags`` and ``dcsb`` need, what upstream's ``set_data`` does)."""
+        that ``tp_flags`` and ``dcsb`` need, what upstream's ``set_data`` does).  Nothing here waits for the
+        device: the constructor returns with the whole setup enqueued.  ``tuning``: fields of ``orie_tuning_t``
+        (``sort_max_blocks``, ``post_blocks``, ``walk_gmem``, ``walk_waves``) for tests and tuning runs."""
         if not torch.cuda.is_available():
             raise RuntimeError("orie_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -159,7 +171,9 @@ class Engine:
         self._ws = None
         self._status = None
         self._want_index = bool(index)
-        self.info = {}
+        self._info = None
+        self._tuning = _lib.Tuning(seg_chunks=int(seg_chunks), **(tuning or {}))
+        self.ens_words = (self.M + 1 + 31) // 32
         with torch.cuda.device(self.device):
             self.stream = stream or torch.cuda.current_stream()
             with torch.cuda.stream(self.stream):
@@ -174,10 +188,10 @@ class Engine:
                         ev_tp.record(match_s)
                     for t in (self.w_tp, self.w_match, self.w_biou, self.s_tp, self.s_match, self.s_biou):
                         t.record_stream(self.stream)
-                    self._build_index(seg_chunks, ev_tp)
+                    self._build_index(ev_tp)
                     self.stream.wait_event(ev_tp)
                 else:
-                    self._pipelined_setup(packed if isinstance(packed, HostPacked) else HostPacked(packed), seg_chunks)
+                    self._pipelined_setup(packed if isinstance(packed, HostPacked) else HostPacked(packed))
 
     def _adopt(self, d):
         self.h2d_bytes = d.nbytes
@@ -185,7 +199,7 @@ class Engine:
             setattr(self, k, getattr(d, k))
         self.Dw, self.Ds, self.G = int(self.w_cls.numel()), int(self.s_cls.numel()), int(self.l_cls.numel())
 
-    def _pipelined_setup(self, hp, seg_chunks):
+    def _pipelined_setup(self, hp):
         """Host -> HBM with the copies overlapped with compute: the small arrays (offsets, classes,
         confidences; all the index sort needs) go first, the boxes (70 % of the bytes, needed only by
         the matcher) follow on the copy stream while the sort already runs; the matcher runs on a side
@@ -217,7 +231,7 @@ class Engine:
             ev_tp.record(match_s)
         for t in (self.w_tp, self.w_match, self.w_biou, self.s_tp, self.s_match, self.s_biou):
             t.record_stream(main)
-        self._build_index(seg_chunks, ev_tp)
+        self._build_index(ev_tp)
         main.wait_event(ev_tp)
 
     # ------------------------------------------------------------------ setup
@@ -242,7 +256,7 @@ class Engine:
         self.w_tp, self.w_match, self.w_biou = run(self.w_box, self.w_cls, self.w_off, self.Dw)
         self.s_tp, self.s_match, self.s_biou = run(self.s_box, self.s_cls, self.s_off, self.Ds)
 
-    def _build_index(self, seg_chunks, tp_ready):
+    def _build_index(self, tp_ready):
         if not self._want_index:
             return
         h = C.c_void_p(0)
@@ -250,11 +264,20 @@ class Engine:
         _lib.check(self.lib.orie_index_build(
             self.M, self.Cn, self.T, self.Dw, self.Ds, self.G, _ptr(self.w_off), _ptr(self.w_cls), _ptr(self.w_conf), _ptr(self.w_tp),
             _ptr(self.s_off), _ptr(self.s_cls), _ptr(self.s_conf), _ptr(self.s_tp), _ptr(self.l_off), _ptr(self.l_cls),
-            int(seg_chunks), ev, self._s(), C.byref(h)))
+            C.byref(self._tuning), ev, self._s(), C.byref(h)))
         self._handle = h
-        info = _lib.IndexInfo()
-        _lib.check(self.lib.orie_index_info(h, C.byref(info)))
-        self.info = {k: int(getattr(info, k)) for k, _ in info._fields_}
+
+    @property
+    def info(self):
+        """Exact sizes of the index (slots, segments, events, ...).  The build is asynchronous; the first access
+        waits for it, and raises if the device rejected the input."""
+        if self._info is None:
+            if not self._handle:
+                return {}
+            info = _lib.IndexInfo()
+            _lib.check(self.lib.orie_index_info(self._handle, C.byref(info)))
+            self._info = {k: int(getattr(info, k)) for k, _ in info._fields_}
+        return self._info
 
     def close(self):
         if self._handle:
@@ -288,7 +311,25 @@ class Engine:
         return out.cpu().numpy()
 
     def workspace_bytes(self, nt: int) -> int:
+        """Exact workspace size for ``nt`` targets (waits for the index build the first time)."""
+        self.info
         return int(self.lib.orie_reward_workspace_bytes(self._handle, int(nt)))
+
+    def workspace_bound(self, nt: int) -> int:
+        """Upper bound of the workspace size, computed without waiting for the device."""
+        return int(self.lib.orie_reward_workspace_bound(self._handle, int(nt)))
+
+    def plan_waves(self, nt: int, budget_bytes: int):
+        """(targets per wave, workspace bytes).  If the host-side upper bound of the workspace fits the budget the whole
+        range runs as one wave and nothing waits for the index build; otherwise the exact sizes are fetched (one
+        synchronisation) and the targets are cut into waves that fit."""
+        if nt <= 0:
+            return 0, 256
+        bound = self.workspace_bound(nt)
+        if bound <= budget_bytes:
+            return nt, bound
+        wave = self.wave_size(nt, budget_bytes)
+        return wave, self.workspace_bytes(wave)
 
     def wave_size(self, nt: int, budget_bytes: int) -> int:
         """Largest multiple of 32 targets whose workspace fits the budget."""
@@ -317,7 +358,7 @@ class Engine:
         nt = self.M - t0 if nt is None else int(nt)
         N = clamp_ensemble(self.M, num_ensemble)
         dev = self.device
-        words = self.info["ens_words"]
+        words = self.ens_words
         reward = torch.empty(max(nt, 1), dtype=torch.float64, device=dev)
         det = torch.empty((max(nt, 1), 3), dtype=torch.float64, device=dev) if detail else None
         if nt == 0:
@@ -331,8 +372,8 @@ class Engine:
                 if em.device != dev:
                     em = (em.pin_memory() if em.numel() else em).to(dev, non_blocking=True)
                 em = em.to(torch.int32).contiguous()
-            wave = self.wave_size(nt, workspace_budget)
-            ws = self._workspace(self.workspace_bytes(wave))
+            wave, ws_bytes = self.plan_waves(nt, workspace_budget)
+            ws = self._workspace(ws_bytes)
             bits = torch.empty((wave, words), dtype=torch.int32, device=dev)
             status = torch.zeros(1, dtype=torch.int32, device=dev)
             for a in range(0, nt, wave):
@@ -352,7 +393,7 @@ class Engine:
         """uint32[nt, ens_words] bitmaps the device-side draw produces for (seed, target)."""
         nt = self.M - t0 if nt is None else int(nt)
         N = clamp_ensemble(self.M, num_ensemble)
-        bits = torch.empty((max(nt, 1), self.info["ens_words"]), dtype=torch.int32, device=self.device)
+        bits = torch.empty((max(nt, 1), self.ens_words), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             _lib.check(self.lib.orie_ensemble_sample(self._handle, t0, nt, N, int(seed) & (2**64 - 1), _ptr(bits), self._s()))
         return bits[:nt].cpu().numpy().view(np.uint32)
@@ -365,7 +406,7 @@ class Engine:
         dev = self.device
         with torch.cuda.device(dev), torch.cuda.stream(self.stream):
             ws = self._workspace(self.workspace_bytes(nt))
-            bits = torch.empty((nt, self.info["ens_words"]), dtype=torch.int32, device=dev)
+            bits = torch.empty((nt, self.ens_words), dtype=torch.int32, device=dev)
             reward = torch.empty(nt, dtype=torch.float64, device=dev)
             _lib.check(self.lib.orie_ensemble_sample(self._handle, t0, nt, N, int(seed) & (2**64 - 1), _ptr(bits), self._s()))
             ms = (C.c_float * 4)()
@@ -390,9 +431,9 @@ class Engine:
                 if em.device != dev:
                     em = (em.pin_memory() if em.numel() else em).to(dev, non_blocking=True)
                 em = em.to(torch.int32).contiguous()
-            wave = self.wave_size(nt, workspace_budget)
-            ws = self._workspace(self.workspace_bytes(wave))
-            bits = torch.empty((wave, self.info["ens_words"]), dtype=torch.int32, device=dev)
+            wave, ws_bytes = self.plan_waves(nt, workspace_budget)
+            ws = self._workspace(ws_bytes)
+            bits = torch.empty((wave, self.ens_words), dtype=torch.int32, device=dev)
             status = torch.zeros(1, dtype=torch.int32, device=dev)
             for a in range(0, nt, wave):
                 n = min(wave, nt - a)
@@ -408,10 +449,14 @@ class Engine:
         return sums[:nt]
 
     def check_status(self):
+        """Raise for errors only the device could see: bad explicit ensembles, input the index build rejected, a
+        workspace too small for the event lists.  Synchronises."""
         st = int(self._status.item()) if self._status is not None else 0
         if st:
             raise _lib.OrieError(5, "ensemble index out of range, equal to its target, or repeated"
                                     f" (status {st})")
+        if self._handle:
+            _lib.check(self.lib.orie_index_status(self._handle))
 
     def orie(self, num_ensemble: int, ens_matrix=None, seed: int = 0, t0: int = 0, nt=None, **kw) -> np.ndarray:
         out = self.orie_device(num_ensemble, ens_matrix, seed, t0, nt, **kw)

@@ -15,12 +15,23 @@
  *     ones owned by an orie_index_t (created by orie_index_build, released by
  *     orie_index_destroy).  Scratch for the reward pass is a caller-provided
  *     workspace (orie_reward_workspace_bytes);
- *   - work is enqueued on the given CUDA stream and is asynchronous, except
- *     orie_index_build and the *_host helpers, which synchronise that stream;
+ *   - work is enqueued on the given CUDA stream and is asynchronous —
+ *     orie_index_build included: nothing on the path from the packed dataset
+ *     to the reward vector waits for the device, so the whole job can be
+ *     enqueued (or captured in a CUDA graph) in one go.  Only the functions
+ *     that REPORT device-side facts synchronise: orie_index_info,
+ *     orie_index_status, orie_reward_workspace_bytes, orie_reward_profile;
  *   - return value 0 = ORIE_OK, otherwise an ORIE_E* code; orie_last_error()
- *     returns a thread-local message for the last failure on this thread;
- *   - no global mutable state: one host thread per GPU may drive its own
- *     index/workspace concurrently with others.
+ *     returns a thread-local message for the last failure on this thread.
+ *     Errors that only the device can detect (class id out of range, offsets
+ *     that do not match the row counts, a workspace too small for the event
+ *     lists) are sticky in the index: the reward pass then computes nothing
+ *     and stores NaN, and orie_index_status / orie_index_info return the code;
+ *   - no global mutable state visible to the caller: one host thread per GPU
+ *     may drive its own index/workspace concurrently with others.  The index
+ *     allocates from a stream-ordered memory pool PRIVATE to this library (one
+ *     per device, created on first use); the device's default pool is never
+ *     touched.
  *
  * Data layout ("packed dataset")
  *   M images, C dense class ids [0,C), T IoU thresholds (1..16).
@@ -105,15 +116,34 @@ typedef struct {
     int64_t device_bytes;                     /* bytes owned by the index */
 } orie_index_info_t;
 
+/* Per-index tuning / test knobs (all zero = defaults; nothing is read from the environment). */
+typedef struct {
+    int32_t seg_chunks;       /* chunks per segment; 0 = auto; at most 2047 (clamped) */
+    int32_t sort_max_blocks;  /* cap on the CTAs of the cooperative sort (few CTAs force its multi-tile path) */
+    int32_t post_blocks;      /* cap on the CTAs of the post-layout kernel */
+    int32_t walk_gmem;        /* != 0: keep the walk's membership tables in global memory even if they fit shared memory */
+    int32_t ap_mode;          /* AP kernel variant (measurement knob, results identical up to summation order): 0 = default */
+    int32_t reserved;
+    double walk_waves;        /* resident-block waves the walk grid is sized for; 0 = default (2) */
+} orie_tuning_t;
+
+/* Asynchronous: returns as soon as the build is enqueued on `stream`; *out is usable by every call below at once
+ * (they are ordered behind the build on the same stream; on another stream, order them yourself). */
 int orie_index_build(int64_t M, int64_t C, int T,
                      int64_t num_weak, int64_t num_strong, int64_t num_labels, /* == off[M] of each block */
                      const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                      const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
                      const int64_t *l_off, const int32_t *l_cls,
-                     int seg_chunks /* 0 = auto; at most 2047 (clamped) */, orie_event_t tp_ready /* nullable */,
+                     const orie_tuning_t *tuning /* nullable */, orie_event_t tp_ready /* nullable */,
                      orie_stream_t stream, orie_index_t **out);
 void orie_index_destroy(orie_index_t *idx);
+/* Waits for the build (first call only), then reports the exact sizes; returns the build's error code if the device
+ * rejected the input (ORIE_EDATA: class id outside [0, C) or offsets inconsistent with the row counts; ORIE_ELIMIT:
+ * more than 65535 rows in one image file). */
 int orie_index_info(const orie_index_t *idx, orie_index_info_t *info);
+/* Waits for the index's stream; ORIE_OK, the build's error code, or ORIE_EWORKSPACE if a reward call since the
+ * build was given a workspace too small for the event lists (its outputs are NaN). */
+int orie_index_status(const orie_index_t *idx);
 
 /*
  * Ensembles.  An ensemble is a bitmap over images: uint32[ens_words] per
@@ -146,7 +176,11 @@ int orie_ensemble_sample(const orie_index_t *idx, int64_t t0, int64_t nt, int64_
  * detail (nullable): f64[nt,3] = (sum of weak APs, sum of strong APs, number
  * of ground-truth classes) per target, for parity checks.
  */
+/* orie_reward_workspace_bytes: exact size (waits for the build the first time).  orie_reward_workspace_bound: an
+ * upper bound computed on the host without waiting (events <= min(weak rows, labels x T)); any size in between is
+ * accepted as long as the event lists fit, which the reward pass checks on the device. */
 size_t orie_reward_workspace_bytes(const orie_index_t *idx, int64_t nt);
+size_t orie_reward_workspace_bound(const orie_index_t *idx, int64_t nt);
 int orie_reward(const orie_index_t *idx, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
                 void *workspace, size_t workspace_bytes, double *reward, double *detail, orie_stream_t stream);
 
@@ -158,6 +192,10 @@ int orie_reward(const orie_index_t *idx, int64_t t0, int64_t nt, const uint32_t 
  */
 int orie_reward_sums(const orie_index_t *idx, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
                      void *workspace, size_t workspace_bytes, double *sums, int full, orie_stream_t stream);
+
+/* reward[r] = (N+1) * (sums[r,1] - sums[r,0]) / (sums[r,2] * T), 0 where sums[r,2] == 0: the last step of a class-sharded
+ * run, after the per-target sums of the ranks have been added (reward.py:50,86).  sums f64[nt,3], reward f64[nt]. */
+int orie_rewards_from_sums(const double *sums, int64_t nt, int T, int64_t N, double *reward, orie_stream_t stream);
 
 /*
  * Same as orie_reward / orie_reward_sums (reward or sums may be NULL, not both), with CUDA events recorded on
@@ -180,6 +218,14 @@ int orie_reward_profile(const orie_index_t *idx, int64_t t0, int64_t nt, const u
 size_t orie_rank_workspace_bytes(int64_t M);
 int orie_rank_normalize(const double *reward, const uint8_t *val_mask, int64_t M, double *out,
                         void *workspace, size_t workspace_bytes, orie_stream_t stream);
+
+/*
+ * Measurement aid (profiles/ap_depths.py): orie_reward with the AP kernel also recording, for every (target, class,
+ * threshold) it integrates, the trip counts of the reverse sweep and of its shared-state tail loop:
+ * depths uint32[nt][C][T][2], zero-initialised by the caller (entries of skipped classes stay zero).
+ */
+int orie_reward_depths(const orie_index_t *idx, int64_t t0, int64_t nt, const uint32_t *ens_bits, int64_t N,
+                       void *workspace, size_t workspace_bytes, double *reward, uint32_t *depths, orie_stream_t stream);
 
 /* Number of kernels this library has launched in this process (all threads). */
 long long orie_launch_count(void);

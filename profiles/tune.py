@@ -11,7 +11,7 @@ import bench
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "coco5000"
 segs = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0,16,32,64,128".split(","))]
-ds, pk, N, iouv = bench.dataset(workload)
+ds, pk, method, N, iouv = bench.dataset(workload)
 dev = torch.device("cuda:0")
 hp = HostPacked(pk)
 dp = DevicePacked(hp, dev)
@@ -19,9 +19,7 @@ torch.cuda.synchronize()
 waves = os.environ.get("TUNE_WAVES", "").split(",") if os.environ.get("TUNE_WAVES") else [None]
 for sc in [(a, w) for a in segs for w in waves]:
     sc, wv = sc
-    if wv is not None:
-        os.environ["ORIE_WALK_WAVES"] = wv
-    eng = Engine(dp, iouv=iouv, seg_chunks=sc)
+    eng = Engine(dp, iouv=iouv, seg_chunks=sc, tuning=dict(walk_waves=float(wv)) if wv is not None else None)
     rows = []
     for rep in range(6):
         rows.append(eng.profile_reward(N, seed=rep))

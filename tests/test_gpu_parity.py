@@ -110,7 +110,7 @@ def test_bad_ensemble_is_reported():
     eng.close()
 
 
-def test_global_memory_membership_table_matches(monkeypatch):
+def test_global_memory_membership_table_matches():
     """Datasets beyond ~58 k images keep the 32-target membership table in global memory instead of shared
     memory; force that path on a small dataset and demand identical bits."""
     M, N = 130, 50
@@ -118,10 +118,8 @@ def test_global_memory_membership_table_matches(monkeypatch):
     eng = _engine(pk, O.IOU_05_095)
     em = O.ensemble_matrix(M, N, 9)
     ref = eng.orie(N, ens_matrix=em)
-    monkeypatch.setenv("ORIE_WALK_GMEM", "1")
-    eng2 = _engine(pk, O.IOU_05_095)
+    eng2 = _engine(pk, O.IOU_05_095, tuning=dict(walk_gmem=1))
     got = eng2.orie(N, ens_matrix=em)
-    monkeypatch.delenv("ORIE_WALK_GMEM")
     assert np.array_equal(ref, got)
     eng.close(); eng2.close()
 
@@ -154,7 +152,7 @@ def test_class_sharded_sums_add_up():
     assert np.array_equal(a, b)
 
 
-def test_multi_tile_sort_path_matches(monkeypatch):
+def test_multi_tile_sort_path_matches():
     """The cooperative radix sort keeps a CTA's items in registers when they fit one tile; larger ranges (the 50k
     sweep) stream tile by tile.  Force that path on a small dataset (2 CTAs for ~35 k detections) and demand
     identical bits, TP flags included."""
@@ -164,11 +162,9 @@ def test_multi_tile_sort_path_matches(monkeypatch):
     eng = _engine(pk, O.IOU_05_095)
     ref, ref_detail = eng.orie(N, ens_matrix=em, detail=True)
     ref_dev = eng.orie(N, seed=17)
-    monkeypatch.setenv("ORIE_SORT_MAX_BLOCKS", "2")
-    eng2 = _engine(pk, O.IOU_05_095)
+    eng2 = _engine(pk, O.IOU_05_095, tuning=dict(sort_max_blocks=2))
     got, got_detail = eng2.orie(N, ens_matrix=em, detail=True)
     got_dev = eng2.orie(N, seed=17)
-    monkeypatch.delenv("ORIE_SORT_MAX_BLOCKS")
     assert eng.info == eng2.info
     assert np.array_equal(ref, got) and np.array_equal(ref_detail, got_detail) and np.array_equal(ref_dev, got_dev)
     eng.close(); eng2.close()
@@ -223,3 +219,51 @@ def test_images_with_more_rows_than_the_ranking_stage():
     wd, sd, lc = oracle_cache(pk, O.IOU_05_095)
     assert np.abs(got - O.orie_all(wd, sd, lc, em)).max() < 1e-9
     eng.close()
+
+
+def test_device_detected_errors_are_sticky_and_reported():
+    """The index build is asynchronous: input only the device can reject (a class id outside [0, C)) and a workspace
+    too small for the event lists surface through the index status — the rewards are NaN, never silently wrong."""
+    import ctypes as C
+    import torch
+    from orie_b200 import _lib
+    from orie_b200._lib import OrieError
+    M, N = 64, 10
+    _, pk = make_packed(M=M, seed=3)
+    good = _engine(pk, O.IOU_05)
+    ref = good.orie(N, seed=5)
+    bad_cls = pk.w_cls.copy()
+    bad_cls[7] = pk.num_classes + 3
+    import dataclasses
+    bad = _engine(dataclasses.replace(pk, w_cls=bad_cls), O.IOU_05)
+    out = bad.orie_device(N, seed=5)
+    assert torch.isnan(out).all()
+    with pytest.raises(OrieError):
+        bad.check_status()
+    with pytest.raises(OrieError):
+        bad.info
+    bad.close()
+    # a workspace below the exact size: rejected on the host once the sizes are known ...
+    lib = good.lib
+    exact = good.workspace_bytes(M)
+    assert good.workspace_bound(M) >= exact
+    ws = torch.empty(exact, dtype=torch.uint8, device="cuda")
+    bits = torch.from_numpy(good.sample_bits(N, seed=5).view(np.int32)).cuda()
+    rw = torch.empty(M, dtype=torch.float64, device="cuda")
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    small = exact - 4096 * 64
+    if good.info["events"] > 0 and small > 0:
+        assert lib.orie_reward(good._handle, 0, M, C.c_void_p(bits.data_ptr()), N, C.c_void_p(ws.data_ptr()), small,
+                               C.c_void_p(rw.data_ptr()), C.c_void_p(0), s) == 4       # ORIE_EWORKSPACE
+    _lib.check(lib.orie_reward(good._handle, 0, M, C.c_void_p(bits.data_ptr()), N, C.c_void_p(ws.data_ptr()), exact,
+                               C.c_void_p(rw.data_ptr()), C.c_void_p(0), s))
+    assert np.array_equal(rw.cpu().numpy(), ref)
+    # ... and on the device when the call is enqueued before the host knows them
+    fresh = _engine(pk, O.IOU_05)
+    if good.info["events"] > 0 and small > 0:
+        rc = lib.orie_reward(fresh._handle, 0, M, C.c_void_p(bits.data_ptr()), N, C.c_void_p(ws.data_ptr()), small,
+                             C.c_void_p(rw.data_ptr()), C.c_void_p(0), s)
+        if rc == 0:        # the build had not been waited for: the device flags it
+            assert torch.isnan(rw).all()
+            assert lib.orie_index_status(fresh._handle) == 4
+    fresh.close(); good.close()
