@@ -19,7 +19,7 @@ SYMBOLS = [
     "orie_ensemble_from_indices", "orie_ensemble_sample",
     "orie_reward_workspace_bytes", "orie_reward_workspace_bound", "orie_reward", "orie_reward_sums", "orie_rewards_from_sums",
     "orie_reward_profile", "orie_reward_depths", "orie_launch_count",
-    "orie_rank_workspace_bytes", "orie_rank_normalize",
+    "orie_rank_workspace_bytes", "orie_rank_normalize", "orie_dcsb_fit_workspace_bytes", "orie_dcsb_fit",
 ]
 
 
@@ -36,7 +36,7 @@ class IndexInfo(C.Structure):
 
 class Tuning(C.Structure):
     _fields_ = [("seg_chunks", C.c_int32), ("sort_max_blocks", C.c_int32), ("post_blocks", C.c_int32),
-                ("walk_gmem", C.c_int32), ("ap_mode", C.c_int32), ("reserved", C.c_int32), ("walk_waves", C.c_double)]
+                ("walk_gmem", C.c_int32), ("ap_mode", C.c_int32), ("sort_lsd", C.c_int32), ("walk_waves", C.c_double)]
 
 
 class OrieError(RuntimeError):
@@ -104,6 +104,10 @@ def load():
     lib.orie_rank_workspace_bytes.argtypes = [i64]
     lib.orie_rank_normalize.restype = C.c_int
     lib.orie_rank_normalize.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
+    lib.orie_dcsb_fit_workspace_bytes.restype = C.c_size_t
+    lib.orie_dcsb_fit_workspace_bytes.argtypes = [i64, i64]
+    lib.orie_dcsb_fit.restype = C.c_int
+    lib.orie_dcsb_fit.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp, C.POINTER(C.c_double), i32, i32, vp, vp, vp, C.c_size_t, vp]
     lib.orie_launch_count.restype = C.c_longlong
     lib.orie_launch_count.argtypes = []
     _LIB = lib

@@ -197,6 +197,52 @@ def rank_normalize(reward, val_mask=None, device=None) -> np.ndarray:
     return out.cpu().numpy()
 
 
+def fit_dcsb(packed, reward, val_mask=None, area_steps=None, n_count: int = 10, device=None) -> dict:
+    """The DCSB baseline estimator of one cross-validation fold, as ``baseline.py:67-152`` (``fit_dcsb``) computes it
+    from the weak detector's outputs: confidence threshold by bisection, grid search over (object count, smallest
+    area) thresholds on the train rows, offloading decisions for every image.
+
+    ``packed``: the ``Packed`` dataset (its weak block and label counts are used); ``reward``: the reward vector
+    (binarised ``> 0`` as ``baseline.py:166``); ``val_mask``: bool[M] validation rows of the fold (None = all train).
+    Returns ``conf_thresh, num_thresh, area_thresh, train_est, val_est, est`` (``est`` = decisions in image order).
+    Runs on the GPU (``orie_dcsb_fit``)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("orie_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    M, D = int(packed.num_images), int(len(packed.w_cls))
+    reward = np.asarray(reward)
+    if reward.shape != (M,):
+        raise ValueError(f"reward must have shape ({M},), got {reward.shape}")
+    vm = np.zeros(M, dtype=bool) if val_mask is None else np.ascontiguousarray(val_mask, dtype=bool)
+    if vm.shape != (M,):
+        raise ValueError(f"val_mask must have shape ({M},), got {vm.shape}")
+    steps = np.ascontiguousarray(np.arange(0.2, 0.9, 0.01) if area_steps is None else area_steps, dtype=np.float64)
+
+    def up(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    box, conf, off = up(packed.w_box), up(packed.w_conf), up(packed.w_off)
+    mask = up(vm.view(np.uint8))
+    labels = up(np.diff(packed.l_off).astype(np.int64))
+    r01 = up(np.where(reward > 0, 1, 0).astype(np.int64))
+    model = torch.zeros(4, dtype=torch.float64, device=dev)
+    est = torch.zeros(M, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        ws = torch.empty(int(lib.orie_dcsb_fit_workspace_bytes(M, D)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.orie_dcsb_fit(C.c_void_p(box.data_ptr()), C.c_void_p(conf.data_ptr()), C.c_void_p(off.data_ptr()), M, D,
+                                     C.c_void_p(mask.data_ptr()), C.c_void_p(labels.data_ptr()), C.c_void_p(r01.data_ptr()),
+                                     steps.ctypes.data_as(C.POINTER(C.c_double)), len(steps), int(n_count),
+                                     C.c_void_p(model.data_ptr()), C.c_void_p(est.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    m, e = model.cpu().numpy(), est.cpu().numpy()
+    return {"conf_thresh": float(m[0]), "num_thresh": int(m[1]), "area_thresh": float(m[2]), "train_hits": int(m[3]),
+            "train_est": e[~vm], "val_est": e[vm], "est": e}
+
+
 def save_rewards(save_dir, method, num_ensemble, reward, seconds):
     """reward.py:90-92: ``orie{N}.npz`` (N as typed on the command line, not the
     clamped value) or ``dcsb.npz`` with keys ``reward`` and ``time``."""

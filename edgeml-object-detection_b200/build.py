@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liborie_b200.so")
-SOURCES = ["api.cu", "sort.cu", "match.cu", "index.cu", "reward.cu", "rank.cu"]
+SOURCES = ["api.cu", "sort.cu", "match.cu", "index.cu", "reward.cu", "rank.cu", "dcsb_fit.cu"]
 HEADERS = ["common.cuh", "coop.cuh", "index.cuh", os.path.join("..", "..", "include", "orie_b200.h")]
 IO_LIB = os.path.join(HERE, "liborie_io.so")
 IO_SOURCES = ["loader.cpp"]

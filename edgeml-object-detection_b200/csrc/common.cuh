@@ -74,6 +74,36 @@ struct SortJob {
     unsigned *bar = nullptr;
     int64_t per = 0;
 };
+// ---- bucket sort (sort.cu): the dataset sort of the index build -------------
+// Sorts the ids [0, n) by (class, 64-bit key, id) without a pass per key byte: ONE pass bins every item by
+// (class, leading varying key bits), consecutive bins are packed into buckets of a few hundred items, items are
+// scattered to their bucket with atomics, and every bucket is sorted on its own by a bitonic network — by one warp
+// in registers (<= 256 items) or by one CTA in shared memory (<= 8192).  Four grid barriers in all; if the data
+// defeats the binning (a bucket beyond 8192 items: heavy exact ties) the kernel falls back to the LSD radix passes.
+struct BucketSortJob {
+    int64_t n = 0, C = 1;
+    int bits = 0;                      // key bins per class = 1 << bits
+    int cap = 0;                       // items per bucket the packing aims at
+    int64_t nbuckets = 0;              // (n - 1) / cap + 1
+    const uint64_t *key_and_or = nullptr;   // device [2]: AND and OR of all keys (common leading bits are skipped)
+    uint64_t *keys_part = nullptr;     // [n] keys partitioned by bucket (= lsd.keys1)
+    uint32_t *vals_part = nullptr;     // [n] ids partitioned by bucket (= lsd.vals_b)
+    uint32_t *binhist = nullptr;       // [C << bits]   zero on entry
+    uint32_t *bucket_start = nullptr;  // [nbuckets]    zero on entry (holds ~start, maximised)
+    uint32_t *bucket_fill = nullptr;   // [nbuckets]    zero on entry
+    uint32_t *bucket_weak = nullptr;   // [nbuckets]    zero on entry
+    uint32_t *wbefore = nullptr;       // [nbuckets]    ids < split in front of each bucket
+    uint32_t *slice_sum = nullptr;     // [grid]
+    uint32_t *big = nullptr;           // buckets of more than 256 items (sorted by a whole CTA)
+    uint32_t *ctl = nullptr;           // [2]: fell back to the radix passes, number of entries of `big`
+    SortJob lsd;                       // keys0 = input keys, vals_a = sorted ids out, rank_out / rank_split, classes,
+                                       // and the fallback's passes; bar / table / per are filled in by bucket_sort_run
+};
+bool bucket_sort_applicable(int64_t n, int64_t C);
+size_t bucket_sort_scratch_bytes(int64_t n, int64_t C, int max_blocks);
+int bucket_sort_max_blocks(int *out);
+int bucket_sort_run(BucketSortJob job, int64_t C, int max_blocks, void *scratch, cudaStream_t st);
+
 int sort_max_blocks(int *out);                    // co-resident CTAs of the sort kernel on the current device
 size_t sort_scratch_bytes(int max_blocks);
 int sort_add_passes(SortJob *job, int kind, int bit_lo, int bit_hi);

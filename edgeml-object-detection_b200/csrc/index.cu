@@ -50,6 +50,7 @@ struct PrepArgs {
     uint32_t *img_l;     // [G]
     uint32_t *hist;      // [3][C]: weak, labels, strong
     uint32_t *gtcnt;     // [M][C], zero on entry
+    unsigned long long *key_and_or;   // [2]: AND (starts all ones) and OR (starts zero) of all keys
     uint32_t *status;
     int smem_bins;       // 3 * C if the block-local histogram fits in shared memory, else 0
 };
@@ -58,7 +59,9 @@ constexpr int kPrepMaxSmemBins = 12288;   // 48 KB
 
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepArgs a) {
     extern __shared__ uint32_t bins[];
+    __shared__ unsigned long long s_and[kPrepThreads / 32], s_or[kPrepThreads / 32];
     const int lane = threadIdx.x & 31;
+    unsigned long long k_and = ~0ull, k_or = 0ull;
     for (int i = threadIdx.x; i < a.smem_bins; i += kPrepThreads) bins[i] = 0;
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0 && (a.w_off[a.M] != a.Dw || a.s_off[a.M] != a.Ds || a.l_off[a.M] != a.G))
@@ -88,12 +91,25 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepArgs a) {
                 if (ok) atomicAdd(&a.gtcnt[im * a.C + c], 1u);
             } else {
                 const int64_t u = blk == 0 ? r : a.Dw + r;
-                a.keys[u] = conf_desc_key(blk == 0 ? a.w_conf[r] : a.s_conf[r]);
+                const uint64_t key = conf_desc_key(blk == 0 ? a.w_conf[r] : a.s_conf[r]);
+                a.keys[u] = key;
+                k_and &= key; k_or |= key;
                 a.img_all[u] = (uint32_t)im;
             }
         }
     }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        k_and &= __shfl_xor_sync(kFull, k_and, d);
+        k_or |= __shfl_xor_sync(kFull, k_or, d);
+    }
+    if (lane == 0) { s_and[threadIdx.x >> 5] = k_and; s_or[threadIdx.x >> 5] = k_or; }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kPrepThreads / 32; ++w) { k_and &= s_and[w]; k_or |= s_or[w]; }
+        if (k_and != ~0ull) atomicAnd(a.key_and_or, k_and);
+        if (k_or != 0ull) atomicOr(a.key_and_or + 1, k_or);
+    }
     for (int i = threadIdx.x; i < a.smem_bins; i += kPrepThreads)
         if (bins[i]) atomicAdd(&a.hist[i], bins[i]);
 }
@@ -436,7 +452,7 @@ static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
 // — which the host application may be using — is never touched.
 struct DeviceState {
     cudaMemPool_t pool = nullptr;
-    int sort_blocks = 0, post_blocks = 0, sms = 0;
+    int sort_blocks = 0, bucket_blocks = 0, post_blocks = 0, sms = 0;
 };
 static int device_state(DeviceState **out) {
     static std::mutex mu;
@@ -461,6 +477,7 @@ static int device_state(DeviceState **out) {
         ORIE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
         ORIE_CUDA(cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev));
         ORIE_TRY(sort_max_blocks(&s.sort_blocks));
+        ORIE_TRY(bucket_sort_max_blocks(&s.bucket_blocks));
         ORIE_TRY(coop_max_blocks(post_kernel, kPostThreads, 0, &s.post_blocks));
         s.pool = pool;
     }
@@ -523,8 +540,12 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     const int64_t n = Dw + Ds;
     const int64_t Nmax = std::max<int64_t>(std::max(n, G), 1);
     const Dets dets{Dw, Ds, w_cls, s_cls, w_conf, s_conf, w_tp, s_tp};
-    int sort_blocks = ds->sort_blocks, post_blocks = ds->post_blocks;
-    if (tune.sort_max_blocks > 0) sort_blocks = std::min(sort_blocks, tune.sort_max_blocks);
+    int sort_blocks = ds->sort_blocks, bucket_blocks = ds->bucket_blocks, post_blocks = ds->post_blocks;
+    if (tune.sort_max_blocks > 0) {
+        sort_blocks = std::min(sort_blocks, tune.sort_max_blocks);
+        bucket_blocks = std::min(bucket_blocks, tune.sort_max_blocks);
+    }
+    const bool use_buckets = !tune.sort_lsd && bucket_sort_applicable(n, C);
 
     // ---- capacities.  Detection stream: class c takes ceil((cnt_c + 1) / 32) <= cnt_c / 32 + 1 chunks; label stream:
     //      ceil(cnt_c / 32).  A class of nch chunks has ceil(nch / seg_chunks) <= nch / seg_chunks + 1 segments.
@@ -584,6 +605,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     uint32_t *d_cls_off, *d_pad_off, *d_lcls_off, *d_lpad_off;
     uint16_t *own_w_c, *own_s_c, *act_tmp;
     uint32_t *evbase, *act_key;
+    unsigned long long *key_and_or;
     char *scratch;
     TempGuard temp{st};
     A.add(&keys, n);
@@ -608,7 +630,9 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&d_pad_off, C + 1);
     A.add(&d_lcls_off, C + 1);
     A.add(&d_lpad_off, C + 1);
-    A.add(&scratch, (int64_t)std::max(sort_scratch_bytes(sort_blocks), (size_t)post_blocks * 4 + 256));
+    A.add(&key_and_or, 2);
+    A.add(&scratch, (int64_t)std::max(std::max(sort_scratch_bytes(sort_blocks), (size_t)post_blocks * 4 + 256),
+                                      use_buckets ? bucket_sort_scratch_bytes(n, C, bucket_blocks) : (size_t)0));
     ORIE_TRY(A.commit(ds->pool, st, &temp.base, nullptr));
 
     ORIE_CUDA(cudaMemcpyAsync(ix->w_off, w_off, (size_t)(M + 1) * 8, cudaMemcpyDeviceToDevice, st));
@@ -617,13 +641,15 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     ORIE_CUDA(cudaMemsetAsync(hist, 0, (size_t)(3 * C) * 4, st));
     ORIE_CUDA(cudaMemsetAsync(ix->gtcnt, 0, (size_t)(M * C) * 4, st));
     ORIE_CUDA(cudaMemsetAsync(lcursor, 0, (size_t)C * 4, st));
+    ORIE_CUDA(cudaMemsetAsync(key_and_or, 0xff, 8, st));
+    ORIE_CUDA(cudaMemsetAsync(key_and_or + 1, 0, 8, st));
 
     const int cbits = bits_for(C), bbits = bits_for(ix->nbatch);
 
     // ---- prep: images of rows, confidence keys, class histograms, ground-truth counts, validation
     {
         PrepArgs pa{M, C, Dw, Ds, G, w_off, s_off, l_off, w_cls, s_cls, l_cls, w_conf, s_conf,
-                    keys, img_all, img_l, hist, ix->gtcnt, &ix->meta->status, 3 * C <= kPrepMaxSmemBins ? (int)(3 * C) : 0};
+                    keys, img_all, img_l, hist, ix->gtcnt, key_and_or, &ix->meta->status, 3 * C <= kPrepMaxSmemBins ? (int)(3 * C) : 0};
         const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(3 * M, kPrepThreads / 32), 148 * 8);
         prep_kernel<<<grid, kPrepThreads, (size_t)pa.smem_bins * 4, st>>>(pa);
         ORIE_LAUNCH_CHECK();
@@ -648,7 +674,16 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         j.rank_out = wpre; j.rank_split = (uint32_t)Dw;
         ORIE_TRY(sort_add_passes(&j, kDigitKey, 0, 64));
         ORIE_TRY(sort_add_passes(&j, kDigitClass, 0, cbits));
-        ORIE_TRY(sort_run(j, sort_blocks, scratch, st));
+        if (use_buckets) {
+            // one binning pass + per-bucket bitonic sorts (sort.cu); the radix passes above are its fallback
+            BucketSortJob bj;
+            bj.n = n;
+            bj.key_and_or = (const uint64_t *)key_and_or;
+            bj.lsd = j;
+            ORIE_TRY(bucket_sort_run(bj, C, bucket_blocks, scratch, st));
+        } else {
+            ORIE_TRY(sort_run(j, sort_blocks, scratch, st));
+        }
         // the same order regrouped by 32-image batch: the per-batch query lists of the walk (weak and strong rows
         // stay interleaved, ascending by slot)
         SortJob r;

@@ -123,7 +123,7 @@ typedef struct {
     int32_t post_blocks;      /* cap on the CTAs of the post-layout kernel */
     int32_t walk_gmem;        /* != 0: keep the walk's membership tables in global memory even if they fit shared memory */
     int32_t ap_mode;          /* AP kernel variant (measurement knob, results identical up to summation order): 0 = default */
-    int32_t reserved;
+    int32_t sort_lsd;         /* != 0: sort the dataset with the LSD radix passes instead of the bucket sort */
     double walk_waves;        /* resident-block waves the walk grid is sized for; 0 = default (2) */
 } orie_tuning_t;
 
@@ -218,6 +218,26 @@ int orie_reward_profile(const orie_index_t *idx, int64_t t0, int64_t nt, const u
 size_t orie_rank_workspace_bytes(int64_t M);
 int orie_rank_normalize(const double *reward, const uint8_t *val_mask, int64_t M, double *out,
                         void *workspace, size_t workspace_bytes, orie_stream_t stream);
+
+/*
+ * DCSB baseline (the "difficult-case based small-big model" estimator): threshold search on the train rows of one
+ * cross-validation fold and offloading decisions for every image.  Replaces baseline.py:67-152 (fit_dcsb) with the
+ * inputs baseline.py:161-206 builds for --baseline dcsb: the weak detector's outputs (packed block: xyxy boxes,
+ * confidences, offsets; box areas as get_area, baseline.py:155-158), the number of ground-truth objects per image and
+ * the binarised rewards (reward > 0, baseline.py:166).
+ *   val_mask u8[M] nullable (1 = validation row); label_num, reward01 int64[M]; area_steps_host: host array of the
+ *   area thresholds to try (pass numpy's np.arange(0.2, 0.9, 0.01) verbatim), n_count: count thresholds 1..n_count
+ *   (upstream: 10).
+ *   model f64[4] (device) <- confidence threshold, count threshold, area threshold, train hits of the chosen pair;
+ *   est int64[M] (device) <- decision of every image (upstream's train_est / val_est, split by val_mask).
+ * The confidence bisection (baseline.py:95-106) stops when upstream's tolerance is met; upstream loops forever if it
+ * cannot be met (e.g. no train labels), this entry point stops after 1100 halvings.
+ */
+size_t orie_dcsb_fit_workspace_bytes(int64_t M, int64_t num_weak);
+int orie_dcsb_fit(const double *w_box, const double *w_conf, const int64_t *w_off, int64_t M, int64_t num_weak,
+                  const uint8_t *val_mask, const int64_t *label_num, const int64_t *reward01,
+                  const double *area_steps_host, int n_area, int n_count,
+                  double *model, int64_t *est, void *workspace, size_t workspace_bytes, orie_stream_t stream);
 
 /*
  * Measurement aid (profiles/ap_depths.py): orie_reward with the AP kernel also recording, for every (target, class,

@@ -162,7 +162,7 @@ def test_multi_tile_sort_path_matches():
     eng = _engine(pk, O.IOU_05_095)
     ref, ref_detail = eng.orie(N, ens_matrix=em, detail=True)
     ref_dev = eng.orie(N, seed=17)
-    eng2 = _engine(pk, O.IOU_05_095, tuning=dict(sort_max_blocks=2))
+    eng2 = _engine(pk, O.IOU_05_095, tuning=dict(sort_max_blocks=2, sort_lsd=1))
     got, got_detail = eng2.orie(N, ens_matrix=em, detail=True)
     got_dev = eng2.orie(N, seed=17)
     assert eng.info == eng2.info
@@ -267,3 +267,35 @@ def test_device_detected_errors_are_sticky_and_reported():
             assert torch.isnan(rw).all()
             assert lib.orie_index_status(fresh._handle) == 4
     fresh.close(); good.close()
+
+
+def test_bucket_sort_agrees_with_the_radix_passes():
+    """The dataset sort of the index build is a bucket sort (one binning pass, per-bucket bitonic sorts) with the LSD
+    radix passes as its fallback.  Same order bit for bit on ordinary data, on data with heavy exact confidence ties
+    (buckets beyond a warp's 256 items are sorted by a whole CTA) and on data that defeats the binning altogether
+    (one confidence value for tens of thousands of rows: the kernel falls back to the radix passes)."""
+    from orie_b200 import data, synth
+    from orie_b200.synth import DetectorShape
+    M, N = 120, 40
+    ds = synth.generate(M, 6, 5.0, 0.0, DetectorShape(.6, .08, 250, 300), DetectorShape(.8, .04, 200, 300), 17)
+    base = data.pack(ds.labels, ds.weak, ds.strong)
+    em = O.ensemble_matrix(M, N, 4)
+    cases = {"plain": lambda c: c, "ties": lambda c: np.round(c, 1), "one value": lambda c: np.full_like(c, 0.25)}
+    for name, f in cases.items():
+        import dataclasses
+        pk = dataclasses.replace(base, w_conf=f(base.w_conf), s_conf=f(base.s_conf))
+        a = _engine(pk, O.IOU_05_095)
+        b = _engine(pk, O.IOU_05_095, tuning=dict(sort_lsd=1))
+        ra, da = a.orie(N, ens_matrix=em, detail=True)
+        rb, db = b.orie(N, ens_matrix=em, detail=True)
+        assert a.info == b.info, name
+        assert np.array_equal(ra, rb) and np.array_equal(da, db), name
+        a.close(); b.close()
+    # and against the oracle in the documented tie order, on the tied data
+    pk = dataclasses.replace(base, w_conf=np.round(base.w_conf, 1), s_conf=np.round(base.s_conf, 1))
+    eng = _engine(pk, O.IOU_05_095)
+    got = eng.orie(N, ens_matrix=em)
+    wd, sd, lc = oracle_cache(pk, O.IOU_05_095)
+    want = np.array([_orie_with_the_engine_tie_rule(i, wd, sd, lc, em[i]) for i in range(0, M, 7)])
+    assert np.abs(got[::7] - want).max() < 1e-9
+    eng.close()
