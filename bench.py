@@ -77,6 +77,7 @@ def parse():
                     help="multi-GPU decomposition: classes (whole pipeline shrinks per rank, one all-reduce of 3 doubles "
                          "per target) or targets (index replicated, one all-gather of reward slices)")
     ap.add_argument("--workspace-gb", type=int, default=16, help="reward-pass workspace budget; targets run in waves that fit")
+    ap.add_argument("--no-graph", action="store_true", help="time the plain calls instead of replaying a recorded job")
     return ap.parse_args()
 
 
@@ -370,7 +371,7 @@ def run_b200(args):
     import torch.distributed as dist
     import orie_b200  # noqa: F401
     from orie_b200 import _lib
-    from orie_b200.engine import DevicePacked, Engine, HostPacked, class_shard, pick_shard, rewards_from_sums, shard_range
+    from orie_b200.engine import DevicePacked, Engine, HostPacked, ReplayJob, class_shard, pick_shard, rewards_from_sums, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -463,6 +464,8 @@ def run_b200(args):
         if profile:
             for k, v in zip(("label_walk_ms", "walk_ms", "ap_ms", "finalize_ms"), ms):
                 kernel_ms[k].append(float(v))
+            if job is not None:              # the timed steps were graph replays: phase split from these plain-call passes
+                phase_ms["match_index_ms"].append(e0.elapsed_time(e1))
         elif record:
             phase_ms["match_index_ms"].append(e0.elapsed_time(e1))
             phase_ms["reward_ms"].append(e1.elapsed_time(e2))
@@ -471,13 +474,44 @@ def run_b200(args):
         eng.close()
         return e0.elapsed_time(e2), info
 
+    # The timed steps replay ONE recorded job (CUDA graph: matching + index build + draw + walk + AP, this rank's
+    # share) per step, followed by the collective.  Datasets whose reward pass has to run in waves sized from
+    # device-side facts (the 50k sweep) cannot be recorded and go through the plain calls.
+    job = None
+    if not is_dcsb and not args.no_graph:
+        try:
+            job = ReplayJob(dp, iouv=iouv, num_ensemble=N, t0=t0, nt=nt, sums=by_class, total_images=M,
+                            tuning=dict(seg_chunks=args.seg_chunks), workspace_budget=args.workspace_gb << 30)
+        except RuntimeError as e:
+            if "cannot be recorded" not in str(e):
+                raise
+    replay_info = {}
+
+    def replay_step(seed, record):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = job.run(seed)
+        if by_class:
+            dist.all_reduce(out)
+            gathered[:M].copy_(rewards_from_sums(out, T, Nc))
+        elif world > 1:
+            mine = torch.zeros(per, dtype=torch.float64, device=dev)
+            mine[:nt] = out
+            dist.all_gather_into_tensor(gathered, mine)
+        else:
+            gathered[:M].copy_(out)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1), replay_info
+
+    timed_step = replay_step if job is not None else step
     clocks = ClockSampler(local)
     windows = []
     if rank == 0:
         clocks.start()                      # sampled from the warm-up to the end of the e2e runs
     for w in range(args.warmup):
         flush.fill_(w)
-        step(1000 + w, False)
+        timed_step(1000 + w, False)
     barrier()
     launches0 = lib.orie_launch_count()
     wall0 = time.perf_counter()
@@ -486,13 +520,17 @@ def run_b200(args):
     for k in range(args.steps):
         flush.fill_(k)                      # L2 flush, not timed
         torch.cuda.synchronize()
-        ms, info = step(2000 + k, True)
+        ms, info = timed_step(2000 + k, True)
         dev_ms += ms
     last_seed = 2000 + args.steps - 1
     barrier()
     wall = time.perf_counter() - wall0
     windows.append((wall0, wall0 + wall))
     launches = lib.orie_launch_count() - launches0
+    if job is not None:
+        launches += job.launches_per_replay * args.steps        # kernels inside the replayed graph (counted when it was recorded)
+        job.check_status()
+        info = dict(job.engine.info)
     result_last = (gathered_i if is_dcsb else gathered[:M]).cpu().numpy().copy()       # what the last timed step produced
     if not is_dcsb:
         for k in range(min(args.steps, 5)):     # per-kernel durations for the roofline: same step, events around each kernel, untimed
@@ -656,9 +694,13 @@ def run_b200(args):
                                    f"targets sharded over {world} gpus, index replicated, one all-gather"),
                    "step": ("TP matching (2 detectors) + DCSB count" if is_dcsb else
                             "TP matching (2 detectors) + index build + ensemble draw + membership walk + AP + collective"),
+                   "launch": ("one CUDA-graph replay per step (engine.ReplayJob), then the collective" if job is not None
+                              else "plain C-ABI calls"),
                    "l2": "flushed between steps (256 MiB write, not timed)", "ensembles": "device-side Philox draw, seed per step",
                    "index": {k: info[k] for k in ("slots", "segments", "events", "seg_chunks", "class_groups")} if info else None,
-                   "phase_ms": {k: sum(v) / len(v) for k, v in phase_ms.items() if v}, "wall_s_timed_region": wall,
+                   "phase_ms": {k: sum(v) / len(v) for k, v in phase_ms.items() if v},
+                   "phase_ms_from": "plain-call passes after the timed region" if job is not None else "the timed steps",
+                   "wall_s_timed_region": wall,
                    "host_class_shard_s": shard_s if by_class else None},
         "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pk.nbytes()), "d2h_bytes_per_step": int(M * 8),

@@ -15,8 +15,8 @@ _LIB = None
 c_i64p = C.c_void_p   # device pointers are passed as plain addresses
 SYMBOLS = [
     "orie_last_error", "orie_version", "orie_match", "orie_dcsb",
-    "orie_index_build", "orie_index_destroy", "orie_index_info", "orie_index_status",
-    "orie_ensemble_from_indices", "orie_ensemble_sample",
+    "orie_index_build", "orie_index_sizes", "orie_index_build_into", "orie_index_destroy", "orie_index_info", "orie_index_status",
+    "orie_ensemble_from_indices", "orie_ensemble_sample", "orie_ensemble_sample_dev",
     "orie_reward_workspace_bytes", "orie_reward_workspace_bound", "orie_reward", "orie_reward_sums", "orie_rewards_from_sums",
     "orie_reward_profile", "orie_reward_depths", "orie_launch_count",
     "orie_rank_workspace_bytes", "orie_rank_normalize", "orie_dcsb_fit_workspace_bytes", "orie_dcsb_fit",
@@ -76,6 +76,13 @@ def load():
     lib.orie_index_build.restype = C.c_int
     lib.orie_index_build.argtypes = [i64, i64, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(Tuning), vp, vp,
                                      C.POINTER(vp)]
+    lib.orie_index_sizes.restype = C.c_int
+    lib.orie_index_sizes.argtypes = [i64, i64, i32, i64, i64, i64, C.POINTER(Tuning), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.orie_index_build_into.restype = C.c_int
+    lib.orie_index_build_into.argtypes = [i64, i64, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(Tuning),
+                                          vp, C.c_size_t, vp, C.c_size_t, vp, vp, C.POINTER(vp)]
+    lib.orie_ensemble_sample_dev.restype = C.c_int
+    lib.orie_ensemble_sample_dev.argtypes = [vp, i64, i64, i64, vp, vp, vp]
     lib.orie_index_status.restype = C.c_int
     lib.orie_index_status.argtypes = [vp]
     lib.orie_reward_workspace_bound.restype = C.c_size_t

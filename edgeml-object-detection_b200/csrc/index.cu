@@ -496,20 +496,18 @@ struct Arena {
     void add(Tp **p, int64_t count) {
         items.push_back({(void **)p, (size_t)round_up(std::max<int64_t>(count, 1) * (int64_t)sizeof(Tp), 256)});
     }
-    int commit(cudaMemPool_t pool, cudaStream_t st, void **base, size_t *bytes) {
-        size_t total = 0;
-        for (auto &it : items) total += it.bytes;
-        void *q = nullptr;
-        ORIE_CUDA(cudaMallocFromPoolAsync(&q, std::max<size_t>(total, 256), pool, st));
+    size_t total() const {
+        size_t t = 0;
+        for (auto &it : items) t += it.bytes;
+        return std::max<size_t>(t, 256);
+    }
+    void bind(void *base) {
         size_t at = 0;
         for (auto &it : items) {
-            *it.p = (char *)q + at;
+            *it.p = (char *)base + at;
             at += it.bytes;
         }
-        *base = q;
-        if (bytes) *bytes = total;
         items.clear();
-        return ORIE_OK;
     }
 };
 
@@ -525,9 +523,17 @@ struct TempGuard {
 // The whole build is enqueued on `st` without a single host synchronisation: allocation sizes, launch grids and table
 // strides come from upper bounds the host can compute from (M, C, Dw, Ds, G); what depends on the data stays on the
 // device (IndexMeta).
+// Memory: caller-provided (orie_index_build_into: nothing is allocated, so the build can be captured in a CUDA graph) or
+// taken from the library's pool (orie_index_build).  plan != nullptr: only report the two sizes.
+struct BuildMemory {
+    void *index_mem = nullptr, *temp_mem = nullptr;
+    size_t index_bytes = 0, temp_bytes = 0;
+    bool external = false;
+};
 static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
                  const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
-                 const int64_t *l_off, const int32_t *l_cls, const orie_tuning_t &tune, cudaEvent_t tp_ready, cudaStream_t st) {
+                 const int64_t *l_off, const int32_t *l_cls, const orie_tuning_t &tune, cudaEvent_t tp_ready, cudaStream_t st,
+                 const BuildMemory &mem, size_t *plan /* [2] or nullptr */) {
     const int64_t M = ix->M, C = ix->C;
     const int64_t Dw = ix->Dw, Ds = ix->Ds, G = ix->G;
     if (Dw < 0 || Ds < 0 || G < 0 || Dw >= ((int64_t)1 << 27) || Ds >= ((int64_t)1 << 27) || G >= ((int64_t)1 << 31)) {
@@ -592,13 +598,8 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&ix->lseg_chunk0, ix->SL_cap);
     A.add(&ix->lseg_nch, ix->SL_cap);
     A.add(&ix->lcls_seg0, C + 1);
-    {
-        void *base = nullptr;
-        size_t bytes = 0;
-        ORIE_TRY(A.commit(ds->pool, st, &base, &bytes));
-        ix->allocs[ix->n_allocs++] = base;
-        ix->device_bytes += (int64_t)bytes;
-    }
+    const size_t index_bytes = A.total();
+    Arena Tm;
 
     uint64_t *keys, *keys_tmp;
     uint32_t *vtmp, *img_all, *img_l, *order, *ord_bat, *pos_of_det, *lcursor, *hist, *wpre, *q_of_det, *ownpos;
@@ -608,32 +609,54 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     unsigned long long *key_and_or;
     char *scratch;
     TempGuard temp{st};
-    A.add(&keys, n);
-    A.add(&keys_tmp, n);
-    A.add(&vtmp, Nmax);
-    A.add(&img_all, n);
-    A.add(&img_l, G);
-    A.add(&order, n);
-    A.add(&ord_bat, n);
-    A.add(&pos_of_det, n);
-    A.add(&lcursor, C);
-    A.add(&hist, 3 * C);
-    A.add(&wpre, n);
-    A.add(&q_of_det, n);
-    A.add(&ownpos, n);
-    A.add(&own_w_c, Dw);
-    A.add(&own_s_c, Ds);
-    A.add(&act_tmp, M * C);
-    A.add(&act_key, M * C);
-    A.add(&evbase, ix->nchunks_cap);
-    A.add(&d_cls_off, C + 1);
-    A.add(&d_pad_off, C + 1);
-    A.add(&d_lcls_off, C + 1);
-    A.add(&d_lpad_off, C + 1);
-    A.add(&key_and_or, 2);
-    A.add(&scratch, (int64_t)std::max(std::max(sort_scratch_bytes(sort_blocks), (size_t)post_blocks * 4 + 256),
+    Tm.add(&keys, n);
+    Tm.add(&keys_tmp, n);
+    Tm.add(&vtmp, Nmax);
+    Tm.add(&img_all, n);
+    Tm.add(&img_l, G);
+    Tm.add(&order, n);
+    Tm.add(&ord_bat, n);
+    Tm.add(&pos_of_det, n);
+    Tm.add(&lcursor, C);
+    Tm.add(&hist, 3 * C);
+    Tm.add(&wpre, n);
+    Tm.add(&q_of_det, n);
+    Tm.add(&ownpos, n);
+    Tm.add(&own_w_c, Dw);
+    Tm.add(&own_s_c, Ds);
+    Tm.add(&act_tmp, M * C);
+    Tm.add(&act_key, M * C);
+    Tm.add(&evbase, ix->nchunks_cap);
+    Tm.add(&d_cls_off, C + 1);
+    Tm.add(&d_pad_off, C + 1);
+    Tm.add(&d_lcls_off, C + 1);
+    Tm.add(&d_lpad_off, C + 1);
+    Tm.add(&key_and_or, 2);
+    Tm.add(&scratch, (int64_t)std::max(std::max(sort_scratch_bytes(sort_blocks), (size_t)post_blocks * 4 + 256),
                                       use_buckets ? bucket_sort_scratch_bytes(n, C, bucket_blocks) : (size_t)0));
-    ORIE_TRY(A.commit(ds->pool, st, &temp.base, nullptr));
+    const size_t temp_bytes = Tm.total();
+    if (plan) {
+        plan[0] = index_bytes; plan[1] = temp_bytes;
+        return ORIE_OK;
+    }
+    if (mem.external) {
+        if (mem.index_bytes < index_bytes || mem.temp_bytes < temp_bytes || !mem.index_mem || !mem.temp_mem ||
+            ((uintptr_t)mem.index_mem & 255) || ((uintptr_t)mem.temp_mem & 255)) {
+            set_error("orie_index_build_into: needs %zu + %zu bytes (index, temporaries), 256-byte aligned; got %zu + %zu",
+                      index_bytes, temp_bytes, mem.index_bytes, mem.temp_bytes);
+            return ORIE_EWORKSPACE;
+        }
+        A.bind(mem.index_mem);
+        Tm.bind(mem.temp_mem);
+    } else {
+        void *base = nullptr;
+        ORIE_CUDA(cudaMallocFromPoolAsync(&base, index_bytes, ds->pool, st));
+        ix->allocs[ix->n_allocs++] = base;
+        A.bind(base);
+        ORIE_CUDA(cudaMallocFromPoolAsync(&temp.base, temp_bytes, ds->pool, st));
+        Tm.bind(temp.base);
+    }
+    ix->device_bytes += (int64_t)index_bytes;
 
     ORIE_CUDA(cudaMemcpyAsync(ix->w_off, w_off, (size_t)(M + 1) * 8, cudaMemcpyDeviceToDevice, st));
     ORIE_CUDA(cudaMemcpyAsync(ix->s_off, s_off, (size_t)(M + 1) * 8, cudaMemcpyDeviceToDevice, st));
@@ -725,7 +748,6 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         ORIE_CUDA(cudaLaunchCooperativeKernel((const void *)post_kernel, dim3(blocks), dim3(kPostThreads), args, 0, st));
         ORIE_LAUNCH_CHECK();
     }
-    ORIE_CUDA(cudaEventRecord(ix->ready, st));
     return ORIE_OK;
 }
 
@@ -736,7 +758,7 @@ int resolve(const orie_index *cix) {
         return ix->resolved_rc;
     }
     IndexMeta m;
-    ORIE_CUDA(cudaEventSynchronize(ix->ready));
+    ORIE_CUDA(cudaStreamSynchronize(ix->stream));
     ORIE_CUDA(cudaMemcpy(&m, ix->meta, sizeof(m), cudaMemcpyDeviceToHost));
     ix->P = m.P; ix->nchunks = m.nchunks; ix->S = m.S; ix->Ev = m.Ev;
     ix->PL = m.PL; ix->nchunksL = m.nchunksL; ix->SL = m.SL;
@@ -761,17 +783,17 @@ int resolve(const orie_index *cix) {
 
 using namespace orie;
 
-extern "C" int orie_index_build(int64_t M, int64_t C, int T, int64_t num_weak, int64_t num_strong, int64_t num_labels,
-                                const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
-                                const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
-                                const int64_t *l_off, const int32_t *l_cls, const orie_tuning_t *tuning, orie_event_t tp_ready,
-                                orie_stream_t stream, orie_index_t **out) {
-    if (!out) {
+static int index_create(int64_t M, int64_t C, int T, int64_t num_weak, int64_t num_strong, int64_t num_labels,
+                        const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
+                        const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
+                        const int64_t *l_off, const int32_t *l_cls, const orie_tuning_t *tuning, orie_event_t tp_ready,
+                        orie_stream_t stream, const BuildMemory &mem, size_t *plan, orie_index_t **out) {
+    if (!out && !plan) {
         set_error("orie_index_build: out is NULL");
         return ORIE_EINVAL;
     }
-    *out = nullptr;
-    if (M < 1 || C < 1 || !w_off || !s_off || !l_off) {
+    if (out) *out = nullptr;
+    if (M < 1 || C < 1 || (!plan && (!w_off || !s_off || !l_off))) {
         set_error("orie_index_build: need M >= 1, C >= 1 and the three offset arrays");
         return ORIE_EINVAL;
     }
@@ -798,14 +820,8 @@ extern "C" int orie_index_build(int64_t M, int64_t C, int T, int64_t num_weak, i
     ix->walk_gmem = tune.walk_gmem;
     ix->ap_mode = tune.ap_mode;
     ix->walk_waves = tune.walk_waves;
-    int rc = ORIE_OK;
-    if (cudaEventCreateWithFlags(&ix->ready, cudaEventDisableTiming) != cudaSuccess) {
-        set_error("orie_index_build: cannot create an event");
-        rc = ORIE_ECUDA;
-    }
-    if (rc == ORIE_OK)
-        rc = build(ix, w_off, w_cls, w_conf, w_tp, s_off, s_cls, s_conf, s_tp, l_off, l_cls, tune, tp_ready, stream);
-    if (rc != ORIE_OK) {
+    const int rc = build(ix, w_off, w_cls, w_conf, w_tp, s_off, s_cls, s_conf, s_tp, l_off, l_cls, tune, tp_ready, stream, mem, plan);
+    if (rc != ORIE_OK || plan) {
         orie_index_destroy(ix);
         return rc;
     }
@@ -813,10 +829,45 @@ extern "C" int orie_index_build(int64_t M, int64_t C, int T, int64_t num_weak, i
     return ORIE_OK;
 }
 
+extern "C" int orie_index_build(int64_t M, int64_t C, int T, int64_t num_weak, int64_t num_strong, int64_t num_labels,
+                                const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
+                                const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
+                                const int64_t *l_off, const int32_t *l_cls, const orie_tuning_t *tuning, orie_event_t tp_ready,
+                                orie_stream_t stream, orie_index_t **out) {
+    return index_create(M, C, T, num_weak, num_strong, num_labels, w_off, w_cls, w_conf, w_tp, s_off, s_cls, s_conf, s_tp,
+                        l_off, l_cls, tuning, tp_ready, stream, BuildMemory(), nullptr, out);
+}
+
+extern "C" int orie_index_sizes(int64_t M, int64_t C, int T, int64_t num_weak, int64_t num_strong, int64_t num_labels,
+                                const orie_tuning_t *tuning, size_t *index_bytes, size_t *temp_bytes) {
+    if (!index_bytes || !temp_bytes) {
+        set_error("orie_index_sizes: null output");
+        return ORIE_EINVAL;
+    }
+    size_t plan[2] = {0, 0};
+    ORIE_TRY(index_create(M, C, T, num_weak, num_strong, num_labels, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          nullptr, nullptr, nullptr, nullptr, tuning, nullptr, nullptr, BuildMemory(), plan, nullptr));
+    *index_bytes = plan[0];
+    *temp_bytes = plan[1];
+    return ORIE_OK;
+}
+
+extern "C" int orie_index_build_into(int64_t M, int64_t C, int T, int64_t num_weak, int64_t num_strong, int64_t num_labels,
+                                     const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
+                                     const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
+                                     const int64_t *l_off, const int32_t *l_cls, const orie_tuning_t *tuning,
+                                     void *index_mem, size_t index_bytes, void *temp_mem, size_t temp_bytes,
+                                     orie_event_t tp_ready, orie_stream_t stream, orie_index_t **out) {
+    BuildMemory mem;
+    mem.index_mem = index_mem; mem.index_bytes = index_bytes; mem.temp_mem = temp_mem; mem.temp_bytes = temp_bytes;
+    mem.external = true;
+    return index_create(M, C, T, num_weak, num_strong, num_labels, w_off, w_cls, w_conf, w_tp, s_off, s_cls, s_conf, s_tp,
+                        l_off, l_cls, tuning, tp_ready, stream, mem, nullptr, out);
+}
+
 extern "C" void orie_index_destroy(orie_index_t *ix) {
     if (!ix) return;
     for (int i = 0; i < ix->n_allocs; ++i) cudaFreeAsync(ix->allocs[i], ix->stream);
-    if (ix->ready) cudaEventDestroy(ix->ready);
     delete ix;
 }
 

@@ -80,12 +80,11 @@ struct orie_index {
 
     int64_t device_bytes = 0;
     cudaStream_t stream = nullptr;   // stream the index was built on; its memory is freed on it
-    cudaEvent_t ready = nullptr;     // recorded after the last kernel of the build
     void *allocs[8] = {};
     int n_allocs = 0;
 };
 
 namespace orie {
-// Wait for the build (once), read IndexMeta, cache the exact sizes; returns the build's error code.
+// Wait for the index's stream (once), read IndexMeta, cache the exact sizes; returns the build's error code.
 int resolve(const orie_index *ix);
 }  // namespace orie

@@ -93,12 +93,13 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 constexpr int kSampleWarps = 4;
 template <bool SMEM>
 __global__ void __launch_bounds__(kSampleWarps * 32)
-ens_sample_kernel(int64_t nt, int64_t N, int64_t t0, int64_t M, int64_t words, uint64_t seed,
-                  uint32_t *__restrict__ bits_all) {
+ens_sample_kernel(int64_t nt, int64_t N, int64_t t0, int64_t M, int64_t words, uint64_t seed_value,
+                  const uint64_t *__restrict__ seed_dev, uint32_t *__restrict__ bits_all) {
     extern __shared__ uint32_t sbits[];
     const int64_t r = (int64_t)blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
     if (r >= nt) return;
     const int lane = threadIdx.x & 31;
+    const uint64_t seed = seed_dev ? *seed_dev : seed_value;     // from device memory: the call can be replayed in a CUDA graph
     const int64_t target = t0 + r;
     uint32_t *out = bits_all + r * words;
     uint32_t *bits = SMEM ? sbits + (int64_t)(threadIdx.x >> 5) * words : out;
@@ -792,8 +793,8 @@ extern "C" int orie_ensemble_from_indices(const orie_index_t *ix, int64_t t0, in
     return ORIE_OK;
 }
 
-extern "C" int orie_ensemble_sample(const orie_index_t *ix, int64_t t0, int64_t nt, int64_t N, uint64_t seed,
-                                    uint32_t *ens_bits, orie_stream_t stream) {
+static int ensemble_sample(const orie_index_t *ix, int64_t t0, int64_t nt, int64_t N, uint64_t seed, const uint64_t *seed_dev,
+                           uint32_t *ens_bits, orie_stream_t stream) {
     ORIE_TRY(check_range(ix, t0, nt, "orie_ensemble_sample"));
     if (N < 0 || N > ix->M - 1 || !ens_bits) {
         set_error("orie_ensemble_sample: need 0 <= N <= M-1 and a bitmap buffer");
@@ -803,13 +804,27 @@ extern "C" int orie_ensemble_sample(const orie_index_t *ix, int64_t t0, int64_t 
     const size_t smem = (size_t)kSampleWarps * ix->ens_words * 4;
     const unsigned grid = (unsigned)ceil_div(nt, kSampleWarps);
     if (smem <= 48 * 1024) {
-        ens_sample_kernel<true><<<grid, kSampleWarps * 32, smem, stream>>>(nt, N, t0, ix->M, ix->ens_words, seed, ens_bits);
+        ens_sample_kernel<true><<<grid, kSampleWarps * 32, smem, stream>>>(nt, N, t0, ix->M, ix->ens_words, seed, seed_dev, ens_bits);
     } else {
         ORIE_CUDA(cudaMemsetAsync(ens_bits, 0, (size_t)(nt * ix->ens_words) * 4, stream));
-        ens_sample_kernel<false><<<grid, kSampleWarps * 32, 0, stream>>>(nt, N, t0, ix->M, ix->ens_words, seed, ens_bits);
+        ens_sample_kernel<false><<<grid, kSampleWarps * 32, 0, stream>>>(nt, N, t0, ix->M, ix->ens_words, seed, seed_dev, ens_bits);
     }
     ORIE_LAUNCH_CHECK();
     return ORIE_OK;
+}
+
+extern "C" int orie_ensemble_sample(const orie_index_t *ix, int64_t t0, int64_t nt, int64_t N, uint64_t seed,
+                                    uint32_t *ens_bits, orie_stream_t stream) {
+    return ensemble_sample(ix, t0, nt, N, seed, nullptr, ens_bits, stream);
+}
+
+extern "C" int orie_ensemble_sample_dev(const orie_index_t *ix, int64_t t0, int64_t nt, int64_t N, const uint64_t *seed_dev,
+                                        uint32_t *ens_bits, orie_stream_t stream) {
+    if (!seed_dev) {
+        set_error("orie_ensemble_sample_dev: seed_dev is NULL");
+        return ORIE_EINVAL;
+    }
+    return ensemble_sample(ix, t0, nt, N, 0, seed_dev, ens_bits, stream);
 }
 
 template <bool DETS, int THREADS, bool GMEM>

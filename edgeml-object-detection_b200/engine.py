@@ -113,6 +113,7 @@ def rewards_from_sums(sums, T: int, n_used: int):
 
 
 _SIDE = {}
+_INDEX_SIZES = {}
 
 
 def _side_streams(device):
@@ -151,7 +152,7 @@ class DevicePacked:
 
 class Engine:
     def __init__(self, packed, iouv=IOU_05, device=None, seg_chunks: int = 0, stream=None, index: bool = True,
-                 tuning: dict | None = None):
+                 tuning: dict | None = None, capturing: bool = False):
         """``packed``: ``Packed`` (host numpy), ``HostPacked`` (pinned) or
         ``DevicePacked`` (already in HBM).  Uploads if needed, then runs TP
         matching for both detectors and builds the dataset index (``index=False``: matching only — all
@@ -171,8 +172,9 @@ class Engine:
         self._ws = None
         self._status = None
         self._want_index = bool(index)
+        self._capturing = bool(capturing)      # being recorded in a CUDA graph (ReplayJob): nothing may synchronise
         self._info = None
-        self._tuning = _lib.Tuning(seg_chunks=int(seg_chunks), **(tuning or {}))
+        self._tuning = _lib.Tuning(**{"seg_chunks": int(seg_chunks), **(tuning or {})})
         self.ens_words = (self.M + 1 + 31) // 32
         with torch.cuda.device(self.device):
             self.stream = stream or torch.cuda.current_stream()
@@ -186,8 +188,9 @@ class Engine:
                     with torch.cuda.stream(match_s):
                         self._match(match_s)
                         ev_tp.record(match_s)
-                    for t in (self.w_tp, self.w_match, self.w_biou, self.s_tp, self.s_match, self.s_biou):
-                        t.record_stream(self.stream)
+                    if not self._capturing:
+                        for t in (self.w_tp, self.w_match, self.w_biou, self.s_tp, self.s_match, self.s_biou):
+                            t.record_stream(self.stream)
                     self._build_index(ev_tp)
                     self.stream.wait_event(ev_tp)
                 else:
@@ -217,10 +220,11 @@ class Engine:
             for k in boxes:
                 setattr(self, k, getattr(hp, k).to(dev, non_blocking=True))
             ev_boxes.record(copy_s)
-        for k in _FIELDS:
-            t = getattr(self, k)
-            t.record_stream(main)
-            t.record_stream(match_s)
+        if not self._capturing:
+            for k in _FIELDS:
+                t = getattr(self, k)
+                t.record_stream(main)
+                t.record_stream(match_s)
         self.h2d_bytes = hp.nbytes
         self.Dw, self.Ds, self.G = int(self.w_cls.numel()), int(self.s_cls.numel()), int(self.l_cls.numel())
         main.wait_event(ev_small)
@@ -229,8 +233,9 @@ class Engine:
         with torch.cuda.stream(match_s):
             self._match(match_s)
             ev_tp.record(match_s)
-        for t in (self.w_tp, self.w_match, self.w_biou, self.s_tp, self.s_match, self.s_biou):
-            t.record_stream(main)
+        if not self._capturing:
+            for t in (self.w_tp, self.w_match, self.w_biou, self.s_tp, self.s_match, self.s_biou):
+                t.record_stream(main)
         self._build_index(ev_tp)
         main.wait_event(ev_tp)
 
@@ -261,10 +266,23 @@ class Engine:
             return
         h = C.c_void_p(0)
         ev = C.c_void_p(tp_ready.cuda_event) if tp_ready is not None else C.c_void_p(0)
-        _lib.check(self.lib.orie_index_build(
+        # the index lives in memory owned by this object (torch's allocator), so the build allocates nothing and can be
+        # recorded in a CUDA graph; the temporaries go back to the allocator as soon as the build is enqueued
+        # (stream-ordered reuse)
+        key = (self.M, self.Cn, self.T, self.Dw, self.Ds, self.G, bytes(self._tuning))
+        if key not in _INDEX_SIZES:
+            a, b = C.c_size_t(0), C.c_size_t(0)
+            _lib.check(self.lib.orie_index_sizes(self.M, self.Cn, self.T, self.Dw, self.Ds, self.G, C.byref(self._tuning),
+                                                 C.byref(a), C.byref(b)))
+            _INDEX_SIZES[key] = (int(a.value), int(b.value))
+        index_bytes, temp_bytes = _INDEX_SIZES[key]
+        self._index_mem = torch.empty(index_bytes, dtype=torch.uint8, device=self.device)
+        temp = torch.empty(temp_bytes, dtype=torch.uint8, device=self.device)
+        self._temp_mem = temp if self._capturing else None      # a graph replays the build: its temporaries stay alive with it
+        _lib.check(self.lib.orie_index_build_into(
             self.M, self.Cn, self.T, self.Dw, self.Ds, self.G, _ptr(self.w_off), _ptr(self.w_cls), _ptr(self.w_conf), _ptr(self.w_tp),
             _ptr(self.s_off), _ptr(self.s_cls), _ptr(self.s_conf), _ptr(self.s_tp), _ptr(self.l_off), _ptr(self.l_cls),
-            C.byref(self._tuning), ev, self._s(), C.byref(h)))
+            C.byref(self._tuning), _ptr(self._index_mem), index_bytes, _ptr(temp), temp_bytes, ev, self._s(), C.byref(h)))
         self._handle = h
 
     @property
@@ -274,6 +292,8 @@ class Engine:
         if self._info is None:
             if not self._handle:
                 return {}
+            if self._capturing and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the exact index sizes are not available while the job is being recorded")
             info = _lib.IndexInfo()
             _lib.check(self.lib.orie_index_info(self._handle, C.byref(info)))
             self._info = {k: int(getattr(info, k)) for k, _ in info._fields_}
@@ -350,11 +370,18 @@ class Engine:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def _sample(self, t0, n, N, seed, seed_tensor, bits):
+        if seed_tensor is not None:
+            _lib.check(self.lib.orie_ensemble_sample_dev(self._handle, t0, n, N, _ptr(seed_tensor), _ptr(bits), self._s()))
+        else:
+            _lib.check(self.lib.orie_ensemble_sample(self._handle, t0, n, N, int(seed) & (2**64 - 1), _ptr(bits), self._s()))
+
     def orie_device(self, num_ensemble: int, ens_matrix=None, seed: int = 0, t0: int = 0, nt: int | None = None,
-                    workspace_budget: int = 8 << 30, detail: bool = False):
+                    workspace_budget: int = 8 << 30, detail: bool = False, seed_tensor=None):
         """Rewards of targets [t0, t0+nt) as a device tensor (asynchronous on the
         engine's stream).  ``ens_matrix``: int32[nt, N] explicit ensembles (host or
-        device); otherwise ensembles are drawn on the device from ``seed``."""
+        device); otherwise ensembles are drawn on the device from ``seed`` (or from ``seed_tensor``, a device
+        int64[1] read when the kernel runs)."""
         nt = self.M - t0 if nt is None else int(nt)
         N = clamp_ensemble(self.M, num_ensemble)
         dev = self.device
@@ -382,8 +409,7 @@ class Engine:
                     _lib.check(self.lib.orie_ensemble_from_indices(self._handle, t0 + a, n, _ptr(em[a:a + n]), N,
                                                                    _ptr(bits), _ptr(status), self._s()))
                 else:
-                    _lib.check(self.lib.orie_ensemble_sample(self._handle, t0 + a, n, N, int(seed) & (2**64 - 1),
-                                                             _ptr(bits), self._s()))
+                    self._sample(t0 + a, n, N, seed, seed_tensor, bits)
                 _lib.check(self.lib.orie_reward(self._handle, t0 + a, n, _ptr(bits), N, _ptr(ws), ws.numel(),
                                                 _ptr(reward[a:]), _ptr(det[a:]) if detail else C.c_void_p(0), self._s()))
             self._status = status
@@ -415,7 +441,7 @@ class Engine:
         return dict(label_walk_ms=ms[0], walk_ms=ms[1], ap_ms=ms[2], finalize_ms=ms[3])
 
     def orie_sums_device(self, num_ensemble: int, ens_matrix=None, seed: int = 0, t0: int = 0, nt=None,
-                         workspace_budget: int = 8 << 30, full: bool = False, total_images=None):
+                         workspace_budget: int = 8 << 30, full: bool = False, total_images=None, seed_tensor=None):
         """f64[nt, 3] device tensor (sum of weak APs, sum of strong APs, classes with ground truth) per target.
         ``full=False``: only the difference of the two sums is meaningful.  ``total_images``: ensemble-size clamp
         of the un-sharded dataset (class-sharded runs)."""
@@ -441,8 +467,7 @@ class Engine:
                     _lib.check(self.lib.orie_ensemble_from_indices(self._handle, t0 + a, n, _ptr(em[a:a + n]), N,
                                                                    _ptr(bits), _ptr(status), self._s()))
                 else:
-                    _lib.check(self.lib.orie_ensemble_sample(self._handle, t0 + a, n, N, int(seed) & (2**64 - 1),
-                                                             _ptr(bits), self._s()))
+                    self._sample(t0 + a, n, N, seed, seed_tensor, bits)
                 _lib.check(self.lib.orie_reward_sums(self._handle, t0 + a, n, _ptr(bits), N, _ptr(ws), ws.numel(),
                                                      _ptr(sums[a:]), 1 if full else 0, self._s()))
             self._status = status
@@ -466,6 +491,72 @@ class Engine:
             r = out.cpu().numpy()
         self.check_status()
         return r
+
+
+class ReplayJob:
+    """A whole job — upload (if the dataset is handed in as pinned host memory), TP matching for both detectors, index
+    build, device-side ensemble draw, membership walk, AP, rewards — recorded ONCE in a CUDA graph and replayed with
+    one launch per job.  Nothing on the path waits for the device (the index build is asynchronous and allocates
+    nothing), so the ~40 host calls of a job collapse into a single graph launch; the seed of the draw lives in
+    device memory and is set before each replay.  For repeated jobs of one shape (serving, sweeps over seeds or
+    ensemble sizes); a single job gains nothing from being recorded.
+
+    ``packed``: ``DevicePacked`` (replays start from HBM-resident inputs) or ``HostPacked`` (every replay copies the
+    pinned host arrays — which the caller may overwrite in place between replays — to the device first).
+    ``sums=True`` yields the per-target AP sums f64[nt, 3] instead of rewards (class-sharded multi-GPU runs)."""
+
+    def __init__(self, packed, iouv=IOU_05, num_ensemble: int = 1000, t0: int = 0, nt=None, sums: bool = False,
+                 total_images=None, device=None, tuning: dict | None = None, workspace_budget: int = 16 << 30):
+        if not torch.cuda.is_available():
+            raise RuntimeError("orie_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if isinstance(packed, Packed):
+            packed = HostPacked(packed)
+        if isinstance(packed, DevicePacked) and device is None:
+            device = packed.device
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.sums = bool(sums)
+        args = dict(t0=t0, nt=nt, workspace_budget=workspace_budget)
+        with torch.cuda.device(self.device):
+            self.seed = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+            def job(capturing):
+                eng = Engine(packed, iouv=iouv, device=self.device, tuning=tuning, capturing=capturing)
+                n = eng.M - t0 if nt is None else int(nt)
+                if capturing and n > 0 and eng.workspace_bound(n) > workspace_budget:
+                    raise RuntimeError("the job's workspace bound exceeds the budget: it would have to run in waves sized "
+                                       "from device-side facts, which cannot be recorded")
+                if self.sums:
+                    out = eng.orie_sums_device(num_ensemble, seed_tensor=self.seed, total_images=total_images, **args)
+                else:
+                    out = eng.orie_device(num_ensemble, seed_tensor=self.seed, **args)
+                return eng, out
+
+            # one ordinary run first: the library's one-time initialisation (function attributes, occupancy queries)
+            # must not fall into the recording, and a rejected dataset is reported here
+            eng, _ = job(False)
+            eng.check_status()
+            eng.close()
+            torch.cuda.synchronize(self.device)
+            launches = _lib.load().orie_launch_count()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.engine, self.out = job(True)
+            self.launches_per_replay = int(_lib.load().orie_launch_count() - launches)
+
+    def run(self, seed: int):
+        """Enqueue one job on the current stream; returns the device tensor that will hold its result (the same
+        tensor every time: consume it before the next ``run``)."""
+        with torch.cuda.device(self.device):
+            self.seed.fill_(int(seed) & (2**63 - 1))
+            self.graph.replay()
+        return self.out
+
+    def check_status(self):
+        self.engine.check_status()
+
+    def close(self):
+        self.engine.close()
+        self.graph = None
 
 
 def compute_rewards(packed: Packed, method: str = "orie", num_ensemble: int = 1000, iouv=IOU_05, ens_matrix=None,

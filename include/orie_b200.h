@@ -136,6 +136,19 @@ int orie_index_build(int64_t M, int64_t C, int T,
                      const int64_t *l_off, const int32_t *l_cls,
                      const orie_tuning_t *tuning /* nullable */, orie_event_t tp_ready /* nullable */,
                      orie_stream_t stream, orie_index_t **out);
+/* The same build without any allocation inside — every byte comes from the caller, so the call can be recorded in
+ * a CUDA graph and replayed (index_mem must stay alive as long as the index, temp_mem until the build has run on the
+ * device).  orie_index_sizes reports the two sizes for a dataset shape (upper bounds computed from the row counts). */
+int orie_index_sizes(int64_t M, int64_t C, int T, int64_t num_weak, int64_t num_strong, int64_t num_labels,
+                     const orie_tuning_t *tuning /* nullable */, size_t *index_bytes, size_t *temp_bytes);
+int orie_index_build_into(int64_t M, int64_t C, int T,
+                          int64_t num_weak, int64_t num_strong, int64_t num_labels,
+                          const int64_t *w_off, const int32_t *w_cls, const double *w_conf, const uint16_t *w_tp,
+                          const int64_t *s_off, const int32_t *s_cls, const double *s_conf, const uint16_t *s_tp,
+                          const int64_t *l_off, const int32_t *l_cls,
+                          const orie_tuning_t *tuning /* nullable */,
+                          void *index_mem, size_t index_bytes, void *temp_mem, size_t temp_bytes, /* 256-byte aligned */
+                          orie_event_t tp_ready /* nullable */, orie_stream_t stream, orie_index_t **out);
 void orie_index_destroy(orie_index_t *idx);
 /* Waits for the build (first call only), then reports the exact sizes; returns the build's error code if the device
  * rejected the input (ORIE_EDATA: class id outside [0, C) or offsets inconsistent with the row counts; ORIE_ELIMIT:
@@ -164,6 +177,10 @@ int orie_ensemble_from_indices(const orie_index_t *idx, int64_t t0, int64_t nt, 
                                uint32_t *ens_bits, int32_t *status, orie_stream_t stream);
 int orie_ensemble_sample(const orie_index_t *idx, int64_t t0, int64_t nt, int64_t N, uint64_t seed,
                          uint32_t *ens_bits, orie_stream_t stream);
+/* The same draw with the seed read from device memory when the kernel runs (seed_dev: device uint64[1]), so that a
+ * recorded call can be replayed with another seed. */
+int orie_ensemble_sample_dev(const orie_index_t *idx, int64_t t0, int64_t nt, int64_t N, const uint64_t *seed_dev,
+                             uint32_t *ens_bits, orie_stream_t stream);
 
 /*
  * ORIE rewards of targets [t0, t0+nt):

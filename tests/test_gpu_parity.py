@@ -299,3 +299,41 @@ def test_bucket_sort_agrees_with_the_radix_passes():
     want = np.array([_orie_with_the_engine_tie_rule(i, wd, sd, lc, em[i]) for i in range(0, M, 7)])
     assert np.abs(got[::7] - want).max() < 1e-9
     eng.close()
+
+
+def test_replayed_job_matches_the_plain_calls():
+    """ReplayJob records a whole job (matching, index build, draw, walk, AP) in a CUDA graph; replays with different
+    seeds reproduce what the plain calls compute, from HBM-resident inputs and from pinned host arrays that are
+    overwritten in place between replays."""
+    import torch
+    from orie_b200.engine import DevicePacked, Engine, HostPacked, ReplayJob
+    M, N = 200, 60
+    _, pk = make_packed(M=M, seed=23)
+    eng = _engine(pk, O.IOU_05_095)
+    want = {s: eng.orie(N, seed=s) for s in (1, 2, 77)}
+    want_sums = eng.orie_sums_device(N, seed=2, t0=64, nt=96).cpu().numpy()
+    eng.close()
+    dp = DevicePacked(HostPacked(pk), "cuda")
+    job = ReplayJob(dp, iouv=O.IOU_05_095, num_ensemble=N)
+    assert job.launches_per_replay >= 8
+    for s in (1, 2, 77, 1):
+        got = job.run(s).cpu().numpy()
+        assert np.array_equal(got, want[s])
+    job.check_status()
+    job.close()
+    part = ReplayJob(dp, iouv=O.IOU_05_095, num_ensemble=N, t0=64, nt=96, sums=True)
+    assert np.array_equal(part.run(2).cpu().numpy(), want_sums)
+    part.close()
+    # from pinned host memory: the upload is part of every replay
+    hp = HostPacked(pk)
+    job = ReplayJob(hp, iouv=O.IOU_05_095, num_ensemble=N)
+    assert np.array_equal(job.run(2).cpu().numpy(), want[2])
+    hp.w_conf.mul_(0.5)                       # new data in the same buffers (halving keeps the order, changes DCSB-like counts only)
+    hp.s_conf.copy_(torch.from_numpy(pk.s_conf[::-1].copy()))       # and a really different strong detector
+    import dataclasses
+    pk2 = dataclasses.replace(pk, w_conf=pk.w_conf * 0.5, s_conf=pk.s_conf[::-1].copy())
+    eng = _engine(pk2, O.IOU_05_095)
+    want2 = eng.orie(N, seed=5)
+    eng.close()
+    assert np.array_equal(job.run(5).cpu().numpy(), want2)
+    job.close()

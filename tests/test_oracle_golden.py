@@ -10,7 +10,8 @@ from helpers import O, flat_tp, oracle_cache
 from orie_b200 import data
 from orie_b200.synth import Rows
 
-GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not p.endswith("_testmap.npz"))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith(("dcsb_fit", "rank_norm")) and not p.endswith("_testmap.npz"))
 
 
 def load_case(path):
