@@ -73,9 +73,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="targets in the CPU baseline / parity samples (0 = by workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the timed CPU baseline (the parity check still runs)")
     ap.add_argument("--seg-chunks", type=int, default=0, help="segment length override (0 = engine default)")
-    ap.add_argument("--shard", default="auto", choices=["auto", "classes", "targets"],
-                    help="multi-GPU decomposition: classes (whole pipeline shrinks per rank, one all-reduce of 3 doubles "
-                         "per target) or targets (index replicated, one all-gather of reward slices)")
+    ap.add_argument("--shard", default="auto",
+                    help="multi-GPU decomposition: auto | classes | targets | grid:AxB (A class groups x B target blocks); "
+                         "always one all-reduce of 3 doubles per target")
     ap.add_argument("--workspace-gb", type=int, default=16, help="reward-pass workspace budget; targets run in waves that fit")
     ap.add_argument("--no-graph", action="store_true", help="time the plain calls instead of replaying a recorded job")
     return ap.parse_args()
@@ -371,7 +371,8 @@ def run_b200(args):
     import torch.distributed as dist
     import orie_b200  # noqa: F401
     from orie_b200 import _lib
-    from orie_b200.engine import DevicePacked, Engine, HostPacked, ReplayJob, class_shard, pick_shard, rewards_from_sums, shard_range
+    from orie_b200.engine import (DevicePacked, Engine, HostPacked, ReplayJob, class_shard, combine_sums, rewards_from_sums, shard_of_rank,
+                                  shard_plan)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -389,19 +390,20 @@ def run_b200(args):
     M, T = pk.num_images, len(iouv)
     Nc = max(0, min(N, M - 1))
     is_dcsb = method == "dcsb"
-    by_class = world > 1 and not is_dcsb and pick_shard(pk.num_images, args.shard) == "classes"
+    # class groups x target blocks (engine.shard_plan); one all-reduce of zero-padded per-target sums combines the ranks
+    sharded = world > 1 and not is_dcsb
+    rc_n, rt_n = shard_plan(M, world, args.shard) if sharded else (1, 1)
+    rc, _, t0, nt = shard_of_rank(rank, M, world, args.shard) if sharded else (0, 1, 0, M)
     pk_all = pk
     shard_s = 0.0
-    if by_class:
+    if rc_n > 1:
         ts = time.perf_counter()
-        pk = class_shard(pk_all, rank, world)        # this rank's classes, all images (host-side partition at pack time)
+        pk = class_shard(pk_all, rc, rc_n)           # this rank's classes, all images (host-side partition at pack time)
         shard_s = time.perf_counter() - ts
     hp = HostPacked(pk)                      # pinned once, outside every timed region
     dp = DevicePacked(hp, dev)               # resident in HBM for the `value` steps
-    t0, nt = (0, M) if (by_class or is_dcsb and world == 1) else shard_range(M, rank, world)
-    per = M if by_class else shard_range(M, 0, world)[1]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    gathered = torch.empty(M if by_class else per * world, dtype=torch.float64, device=dev)
+    gathered = torch.empty(M, dtype=torch.float64, device=dev)
     gathered_i = torch.zeros(M, dtype=torch.int64, device=dev)
 
     def barrier():
@@ -433,32 +435,29 @@ def run_b200(args):
         wave, ws_bytes = eng.plan_waves(nt, args.workspace_gb << 30)      # no synchronisation when the bound fits the budget
         ws = eng._workspace(ws_bytes)
         bits = torch.empty((max(wave, 1), eng.ens_words), dtype=torch.int32, device=dev)
-        mine = torch.zeros(per, dtype=torch.float64, device=dev)
-        sums = torch.zeros((M, 3), dtype=torch.float64, device=dev) if by_class else None
+        mine = torch.zeros(max(nt, 1), dtype=torch.float64, device=dev)
+        sums = torch.zeros((max(nt, 1), 3), dtype=torch.float64, device=dev) if sharded else None
         ms = [0.0] * 4
         for a in range(0, nt, max(wave, 1)):            # target waves sized by the workspace budget
             cnt = min(wave, nt - a)
             part = (C.c_float * 4)()
             _lib.check(lib.orie_ensemble_sample(eng._handle, t0 + a, cnt, Nc, seed, C.c_void_p(bits.data_ptr()), s))
-            out_r = C.c_void_p(0) if by_class else C.c_void_p(mine.data_ptr() + 8 * a)
-            out_s = C.c_void_p(sums.data_ptr() + 24 * a) if by_class else C.c_void_p(0)
+            out_r = C.c_void_p(0) if sharded else C.c_void_p(mine.data_ptr() + 8 * a)
+            out_s = C.c_void_p(sums.data_ptr() + 24 * a) if sharded else C.c_void_p(0)
             if profile:      # untimed passes only: events around every kernel, synchronises
                 _lib.check(lib.orie_reward_profile(eng._handle, t0 + a, cnt, C.c_void_p(bits.data_ptr()), Nc,
                                                    C.c_void_p(ws.data_ptr()), ws.numel(), out_r, out_s, 0, s, part))
                 ms = [x + float(y) for x, y in zip(ms, part)]
-            elif by_class:
+            elif sharded:
                 _lib.check(lib.orie_reward_sums(eng._handle, t0 + a, cnt, C.c_void_p(bits.data_ptr()), Nc,
                                                 C.c_void_p(ws.data_ptr()), ws.numel(), out_s, 0, s))
             else:
                 _lib.check(lib.orie_reward(eng._handle, t0 + a, cnt, C.c_void_p(bits.data_ptr()), Nc,
                                            C.c_void_p(ws.data_ptr()), ws.numel(), out_r, C.c_void_p(0), s))
-        if by_class:
-            dist.all_reduce(sums)                       # 3 doubles per target: AP sums are additive over classes
-            gathered[:M].copy_(rewards_from_sums(sums, T, Nc))
-        elif world > 1:
-            dist.all_gather_into_tensor(gathered, mine)
+        if sharded:                                     # 3 doubles per target: AP sums are additive over classes
+            gathered.copy_(combine_sums(sums[:nt], t0, M, T, Nc))
         else:
-            gathered.copy_(mine)
+            gathered.copy_(mine[:M])
         e2.record()
         e2.synchronize()
         if profile:
@@ -480,7 +479,7 @@ def run_b200(args):
     job = None
     if not is_dcsb and not args.no_graph:
         try:
-            job = ReplayJob(dp, iouv=iouv, num_ensemble=N, t0=t0, nt=nt, sums=by_class, total_images=M,
+            job = ReplayJob(dp, iouv=iouv, num_ensemble=N, t0=t0, nt=nt, sums=sharded, total_images=M,
                             tuning=dict(seg_chunks=args.seg_chunks), workspace_budget=args.workspace_gb << 30)
         except RuntimeError as e:
             if "cannot be recorded" not in str(e):
@@ -491,15 +490,10 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = job.run(seed)
-        if by_class:
-            dist.all_reduce(out)
-            gathered[:M].copy_(rewards_from_sums(out, T, Nc))
-        elif world > 1:
-            mine = torch.zeros(per, dtype=torch.float64, device=dev)
-            mine[:nt] = out
-            dist.all_gather_into_tensor(gathered, mine)
+        if sharded:
+            gathered.copy_(combine_sums(out, t0, M, T, Nc))
         else:
-            gathered[:M].copy_(out)
+            gathered.copy_(out)
         e1.record()
         e1.synchronize()
         return e0.elapsed_time(e1), replay_info
@@ -565,20 +559,12 @@ def run_b200(args):
         eng = Engine(hp, iouv=iouv, device=dev, index=not is_dcsb)
         if is_dcsb:
             host = eng.dcsb()
-        elif by_class:
-            sums = eng.orie_sums_device(N, seed=3000 + k, total_images=M).clone()
+        elif sharded:
+            sums = eng.orie_sums_device(N, seed=3000 + k, t0=t0, nt=nt, total_images=M)
             eng.stream.synchronize()
-            dist.all_reduce(sums)
-            host = rewards_from_sums(sums, T, Nc).cpu()
+            host = combine_sums(sums, t0, M, T, Nc).cpu()
         else:
-            mine = torch.zeros(per, dtype=torch.float64, device=dev)
-            if nt > 0:
-                mine[:nt] = eng.orie_device(N, seed=3000 + k, t0=t0, nt=nt)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, mine)
-                host = gathered[:M].cpu()
-            else:
-                host = mine[:M].cpu()
+            host = eng.orie_device(N, seed=3000 + k).cpu()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t_start
         eng.close()
@@ -689,9 +675,8 @@ def run_b200(args):
                    "iou_thresholds": T, "weak_dets": int(len(pk_all.w_cls)), "strong_dets": int(len(pk_all.s_cls)),
                    "labels": int(len(pk_all.l_cls)),
                    "parallelism": ("one gpu" if world == 1 else
-                                   f"classes sharded over {world} gpus (every rank: all targets, its classes), one all-reduce of 3 "
-                                   f"doubles per target" if by_class else
-                                   f"targets sharded over {world} gpus, index replicated, one all-gather"),
+                                   f"{rc_n} class group(s) x {rt_n} target block(s) over {world} gpus (a rank: the rows of its "
+                                   f"classes for all images, the targets of its block), one all-reduce of 3 doubles per target"),
                    "step": ("TP matching (2 detectors) + DCSB count" if is_dcsb else
                             "TP matching (2 detectors) + index build + ensemble draw + membership walk + AP + collective"),
                    "launch": ("one CUDA-graph replay per step (engine.ReplayJob), then the collective" if job is not None
@@ -701,7 +686,7 @@ def run_b200(args):
                    "phase_ms": {k: sum(v) / len(v) for k, v in phase_ms.items() if v},
                    "phase_ms_from": "plain-call passes after the timed region" if job is not None else "the timed steps",
                    "wall_s_timed_region": wall,
-                   "host_class_shard_s": shard_s if by_class else None},
+                   "host_class_shard_s": shard_s if rc_n > 1 else None},
         "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pk.nbytes()), "d2h_bytes_per_step": int(M * 8),
                 "note": "bytes per rank" if world > 1 else "",

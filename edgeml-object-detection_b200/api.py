@@ -15,7 +15,8 @@ from pathlib import Path
 import numpy as np
 
 from . import data
-from .engine import IOU_05, IOU_05_095, Engine, class_shard, clamp_ensemble, pick_shard, rewards_from_sums, shard_range
+from .engine import (IOU_05, IOU_05_095, Engine, class_shard, clamp_ensemble, combine_sums, pick_shard, rewards_from_sums,
+                     shard_of_rank, shard_plan, shard_range)
 
 
 def parse_iou_thresholds(spec) -> np.ndarray:
@@ -88,9 +89,8 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
     overlaps it with the sort, also the upload and TP matching that upstream's timer leaves out (``set_data``).
     File loading is reported separately in ``info`` (``load_s``); ``match_index_s`` is the part of ``seconds``
     spent before the first reward kernel.
-    Under torchrun (WORLD_SIZE > 1) the classes are sharded over the ranks and the
-    per-target AP sums are combined with one NCCL all-reduce; datasets beyond ~28 k images
-    shard the targets instead (one all-gather of reward slices), see ``engine.pick_shard``."""
+    Under torchrun (WORLD_SIZE > 1) the work is split into class groups x target blocks (``engine.shard_plan``:
+    classes only up to ~28 k images) and the per-target AP sums are combined with one NCCL all-reduce."""
     import torch
     method = method.lower()
     if method == "ori":
@@ -126,12 +126,12 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
         dist.broadcast(s, 0)
         seed = int(s.item())
     t = time.perf_counter()
-    # Multi-GPU: every rank keeps all images and its share of the classes (AP sums are additive over classes), runs
-    # the whole pipeline for all targets and one all-reduce of 3 doubles per target combines the ranks.
+    # Multi-GPU: class groups x target blocks (engine.shard_plan); a rank keeps all images but only the rows of its class
+    # group, computes the targets of its block, and one all-reduce of the zero-padded per-target AP sums combines the ranks.
     from .engine import HostPacked
-    by_class = dist is not None and method == "orie" and pick_shard(M, shard) == "classes"
-    by_target = dist is not None and method == "orie" and not by_class
-    eng = Engine(HostPacked(class_shard(pk, rank, world) if by_class else pk), iouv=iouv, device=device,
+    sharded = dist is not None and method == "orie"
+    rc, rc_n, t0, nt = shard_of_rank(rank, M, world, shard) if sharded else (0, 1, 0, M)
+    eng = Engine(HostPacked(class_shard(pk, rc, rc_n) if rc_n > 1 else pk), iouv=iouv, device=device,
                  index=method != "dcsb")
     torch.cuda.synchronize()
     t_match = time.perf_counter() - t
@@ -141,21 +141,11 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
             reward = eng.dcsb().astype(int)
         else:
             em = ensemble_matrix_numpy(M, N, seed) if ensembles == "numpy" else None
-            if by_class:
-                sums = eng.orie_sums_device(N, ens_matrix=em, seed=seed, total_images=M).clone()
+            if sharded:
+                sums = eng.orie_sums_device(N, ens_matrix=None if em is None else em[t0:t0 + nt], seed=seed, t0=t0, nt=nt,
+                                            total_images=M)
                 eng.stream.synchronize()
-                dist.all_reduce(sums)
-                reward = rewards_from_sums(sums, eng.T, clamp_ensemble(M, N)).cpu().numpy()
-            elif by_target:
-                t0, nt = shard_range(M, rank, world)
-                per = shard_range(M, 0, world)[1]
-                mine = torch.zeros(per, dtype=torch.float64, device=eng.device)
-                if nt > 0:
-                    mine[:nt] = eng.orie_device(N, ens_matrix=None if em is None else em[t0:t0 + nt], seed=seed, t0=t0, nt=nt)
-                gathered = torch.empty(per * world, dtype=torch.float64, device=eng.device)
-                eng.stream.synchronize()
-                dist.all_gather_into_tensor(gathered, mine)
-                reward = gathered[:M].cpu().numpy()
+                reward = combine_sums(sums, t0, M, eng.T, clamp_ensemble(M, N)).cpu().numpy()
             else:
                 reward = eng.orie_device(N, ens_matrix=em, seed=seed).cpu().numpy()
             eng.check_status()

@@ -85,13 +85,55 @@ def class_shard(packed: Packed, rank: int, world: int) -> Packed:
 
 
 def pick_shard(num_images: int, shard: str = "auto") -> str:
-    """Multi-GPU decomposition.  ``classes`` shrinks every phase (matching, index, walk, AP) with the rank count and
-    is the better choice while the 32-target membership table of the walk fits shared memory (about 28 k images);
-    beyond that the walk is bound by table lookups that do not shrink with the class count, and ``targets`` wins
-    (measured on the 50 k-image sweep, profiles/)."""
+    """Multi-GPU decomposition by name.  ``classes`` shrinks every phase (matching, index, walk, AP) with the rank count
+    and is the choice while the 32-target membership table of the walk fits shared memory (about 28 k images);
+    beyond that ``auto`` splits both ways (``shard_plan``)."""
     if shard != "auto":
         return shard
-    return "classes" if ((num_images + 1 + 31) // 32) * 32 * 4 <= 112 * 1024 else "targets"
+    return "classes" if ((num_images + 1 + 31) // 32) * 32 * 4 <= 112 * 1024 else "grid"
+
+
+def shard_plan(num_images: int, world: int, shard: str = "auto"):
+    """(class groups Rc, target blocks Rt), Rc * Rt == world.  Rank r works on the classes of group ``r % Rc`` (every
+    image, only the rows of those classes: matching, index build, walk and AP all shrink) and on the targets of block
+    ``r // Rc`` (``shard_range``).  Per-target AP sums are additive over classes, so ONE all-reduce of a zero-padded
+    f64[M, 3] tensor combines every decomposition (``combine_sums``).
+    ``classes`` = (world, 1); ``targets`` = (1, world); ``grid:AxB`` = (A, B); ``auto``: classes up to ~28 k images,
+    beyond that half of the factors of two to the classes (large datasets: the index build is the part that only the
+    class split shrinks, the membership tables of the walk are the part that only the target split shrinks)."""
+    world = int(world)
+    kind = pick_shard(num_images, shard)
+    if kind == "classes":
+        return world, 1
+    if kind == "targets":
+        return 1, world
+    if kind.startswith("grid:"):
+        rc, rt = (int(x) for x in kind[5:].lower().split("x"))
+        if rc * rt != world or rc < 1:
+            raise ValueError(f"shard {kind!r} does not multiply to the world size {world}")
+        return rc, rt
+    rc = 1
+    while (rc * 2) ** 2 <= world and world % (rc * 2) == 0:
+        rc *= 2
+    return rc, world // rc
+
+
+def shard_of_rank(rank: int, num_images: int, world: int, shard: str = "auto"):
+    """(class group, class groups, first target, target count) of ``rank``."""
+    rc_n, rt_n = shard_plan(num_images, world, shard)
+    t0, nt = shard_range(num_images, rank // rc_n, rt_n)
+    return rank % rc_n, rc_n, t0, nt
+
+
+def combine_sums(local_sums, t0: int, num_images: int, T: int, n_used: int, group=None):
+    """The one collective of a multi-GPU run: every rank places the per-target AP sums f64[nt, 3] of ITS classes and ITS
+    target block in a zero tensor f64[M, 3]; one all-reduce adds the class groups and assembles the target blocks; the
+    rewards follow from the sums (``rewards_from_sums``).  Works on CUDA tensors (NCCL) and on CPU tensors (gloo)."""
+    import torch.distributed as dist
+    full = torch.zeros((num_images, 3), dtype=torch.float64, device=local_sums.device)
+    full[t0:t0 + local_sums.shape[0]] = local_sums
+    dist.all_reduce(full, group=group)
+    return rewards_from_sums(full, T, n_used)
 
 
 def rewards_from_sums(sums, T: int, n_used: int):
@@ -562,14 +604,10 @@ class ReplayJob:
 def compute_rewards(packed: Packed, method: str = "orie", num_ensemble: int = 1000, iouv=IOU_05, ens_matrix=None,
                     seed: int = 0, device=None, distributed: bool = False, shard: str = "auto"):
     """Reward vector of the whole dataset (what ``reward.py:main`` computes between its two timers, plus
-    ``set_data``'s matching).  With ``distributed=True`` (under torchrun, NCCL) the work is split over the ranks:
-
-    * ``shard="classes"`` (what ``"auto"`` picks up to ~28 k images): every rank keeps all images but only the detections / labels of its share of
-      the classes, runs the whole pipeline on that shard for ALL targets, and the per-target AP sums (3 doubles per
-      target) are combined with one all-reduce.  Matching, the index build, the walk and the AP sweep all shrink
-      with the rank count.
-    * ``shard="targets"`` (``"auto"`` beyond that): every rank holds the whole dataset and computes a contiguous block of targets; the
-      reward slices are combined with one all-gather (the index build is replicated)."""
+    ``set_data``'s matching).  With ``distributed=True`` (under torchrun, NCCL) the work is split over the ranks as
+    ``shard_plan`` says — class groups x target blocks: a rank keeps all images but only the detections / labels of
+    its class group, runs the whole pipeline on that shard for the targets of its block, and ONE all-reduce of the
+    zero-padded per-target AP sums (3 doubles per target) combines the ranks (``combine_sums``)."""
     method = method.lower()
     if method == "ori":
         method, num_ensemble = "orie", 0
@@ -584,29 +622,14 @@ def compute_rewards(packed: Packed, method: str = "orie", num_ensemble: int = 10
             eng.close()
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
-    shard = pick_shard(M, shard)
-    if shard == "classes":
-        eng = Engine(class_shard(packed, rank, world), iouv=iouv, device=device)
-        try:
-            sums = eng.orie_sums_device(num_ensemble, ens_matrix=ens_matrix, seed=seed, total_images=M).clone()
-            eng.stream.synchronize()
-            dist.all_reduce(sums)
-            eng.check_status()
-            return rewards_from_sums(sums, eng.T, clamp_ensemble(M, num_ensemble)).cpu().numpy()
-        finally:
-            eng.close()
-    eng = Engine(packed, iouv=iouv, device=device)
+    rc, rc_n, t0, nt = shard_of_rank(rank, M, world, shard)
+    eng = Engine(class_shard(packed, rc, rc_n) if rc_n > 1 else packed, iouv=iouv, device=device)
     try:
-        t0, nt = shard_range(M, rank, world)
         sub = None if ens_matrix is None else ens_matrix[t0:t0 + nt]
-        mine = eng.orie_device(num_ensemble, ens_matrix=sub, seed=seed, t0=t0, nt=nt)
-        per = shard_range(M, 0, world)[1]
-        pad = torch.zeros(per, dtype=torch.float64, device=eng.device)
-        pad[:nt] = mine
-        gathered = torch.empty(per * world, dtype=torch.float64, device=eng.device)
+        sums = eng.orie_sums_device(num_ensemble, ens_matrix=sub, seed=seed, t0=t0, nt=nt, total_images=M)
         eng.stream.synchronize()
-        dist.all_gather_into_tensor(gathered, pad)
+        reward = combine_sums(sums, t0, M, eng.T, clamp_ensemble(M, num_ensemble))
         eng.check_status()
-        return gathered[:M].cpu().numpy()
+        return reward.cpu().numpy()
     finally:
         eng.close()
