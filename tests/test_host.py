@@ -108,7 +108,8 @@ def test_shard_ranges_cover_the_targets_once():
 
 def test_shard_mode_follows_the_dataset_size():
     assert engine.pick_shard(5000) == "classes" and engine.pick_shard(28000) == "classes"
-    assert engine.pick_shard(50000) == "targets"
+    assert engine.pick_shard(50000) == "grid"
+    assert engine.shard_plan(5000, 8) == (8, 1) and engine.shard_plan(50000, 8) == (2, 4)
     assert engine.pick_shard(50000, "classes") == "classes" and engine.pick_shard(10, "targets") == "targets"
 
 
