@@ -392,8 +392,8 @@ def run_b200(args):
     is_dcsb = method == "dcsb"
     # class groups x target blocks (engine.shard_plan); one all-reduce of zero-padded per-target sums combines the ranks
     sharded = world > 1 and not is_dcsb
-    rc_n, rt_n = shard_plan(M, world, args.shard) if sharded else (1, 1)
-    rc, _, t0, nt = shard_of_rank(rank, M, world, args.shard) if sharded else (0, 1, 0, M)
+    rc_n, rt_n = shard_plan(M, world, args.shard, pk.num_classes) if sharded else (1, 1)
+    rc, _, t0, nt = shard_of_rank(rank, M, world, args.shard, pk.num_classes) if sharded else (0, 1, 0, M)
     pk_all = pk
     shard_s = 0.0
     if rc_n > 1:

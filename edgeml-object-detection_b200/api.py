@@ -130,7 +130,7 @@ def compute_rewards_from_dirs(weak_dir, strong_dir, label_dir, method="orie", nu
     # group, computes the targets of its block, and one all-reduce of the zero-padded per-target AP sums combines the ranks.
     from .engine import HostPacked
     sharded = dist is not None and method == "orie"
-    rc, rc_n, t0, nt = shard_of_rank(rank, M, world, shard) if sharded else (0, 1, 0, M)
+    rc, rc_n, t0, nt = shard_of_rank(rank, M, world, shard, pk.num_classes) if sharded else (0, 1, 0, M)
     eng = Engine(HostPacked(class_shard(pk, rc, rc_n) if rc_n > 1 else pk), iouv=iouv, device=device,
                  index=method != "dcsb")
     torch.cuda.synchronize()

@@ -85,26 +85,20 @@ def class_shard(packed: Packed, rank: int, world: int) -> Packed:
 
 
 def pick_shard(num_images: int, shard: str = "auto") -> str:
-    """Multi-GPU decomposition by name.  ``classes`` shrinks every phase (matching, index, walk, AP) with the rank count
-    and is the choice while the 32-target membership table of the walk fits shared memory (about 28 k images);
-    beyond that ``auto`` splits both ways (``shard_plan``)."""
-    if shard != "auto":
-        return shard
-    return "classes" if ((num_images + 1 + 31) // 32) * 32 * 4 <= 112 * 1024 else "grid"
+    """Multi-GPU decomposition by name; ``auto`` = ``classes`` (measured best from COCO scale to the 50k-image sweep,
+    profiles/: at 8 GPUs 19 ms by classes, 20 ms as 4 x 2, 26 ms as 2 x 4, 37 ms by targets)."""
+    return "classes" if shard == "auto" else shard
 
 
-def shard_plan(num_images: int, world: int, shard: str = "auto"):
+def shard_plan(num_images: int, world: int, shard: str = "auto", num_classes=None):
     """(class groups Rc, target blocks Rt), Rc * Rt == world.  Rank r works on the classes of group ``r % Rc`` (every
-    image, only the rows of those classes: matching, index build, walk and AP all shrink) and on the targets of block
-    ``r // Rc`` (``shard_range``).  Per-target AP sums are additive over classes, so ONE all-reduce of a zero-padded
-    f64[M, 3] tensor combines every decomposition (``combine_sums``).
-    ``classes`` = (world, 1); ``targets`` = (1, world); ``grid:AxB`` = (A, B); ``auto``: classes up to ~28 k images,
-    beyond that half of the factors of two to the classes (large datasets: the index build is the part that only the
-    class split shrinks, the membership tables of the walk are the part that only the target split shrinks)."""
+    image, only the rows of those classes: upload, matching, index build, walk and AP all shrink) and on the targets
+    of block ``r // Rc`` (``shard_range``).  Per-target AP sums are additive over classes, so ONE all-reduce of a
+    zero-padded f64[M, 3] tensor combines every decomposition (``combine_sums``).
+    ``classes`` (= ``auto``) = (world, 1) — with fewer classes than ranks, the largest divisor of the world size that
+    the classes can fill, the rest going to target blocks; ``targets`` = (1, world); ``grid:AxB`` = (A, B)."""
     world = int(world)
     kind = pick_shard(num_images, shard)
-    if kind == "classes":
-        return world, 1
     if kind == "targets":
         return 1, world
     if kind.startswith("grid:"):
@@ -112,15 +106,18 @@ def shard_plan(num_images: int, world: int, shard: str = "auto"):
         if rc * rt != world or rc < 1:
             raise ValueError(f"shard {kind!r} does not multiply to the world size {world}")
         return rc, rt
-    rc = 1
-    while (rc * 2) ** 2 <= world and world % (rc * 2) == 0:
-        rc *= 2
+    if kind != "classes":
+        raise ValueError(f"unknown shard mode {shard!r}")
+    rc = world
+    if num_classes is not None:
+        while rc > 1 and (rc > int(num_classes) or world % rc):
+            rc -= 1
     return rc, world // rc
 
 
-def shard_of_rank(rank: int, num_images: int, world: int, shard: str = "auto"):
+def shard_of_rank(rank: int, num_images: int, world: int, shard: str = "auto", num_classes=None):
     """(class group, class groups, first target, target count) of ``rank``."""
-    rc_n, rt_n = shard_plan(num_images, world, shard)
+    rc_n, rt_n = shard_plan(num_images, world, shard, num_classes)
     t0, nt = shard_range(num_images, rank // rc_n, rt_n)
     return rank % rc_n, rc_n, t0, nt
 
@@ -622,7 +619,7 @@ def compute_rewards(packed: Packed, method: str = "orie", num_ensemble: int = 10
             eng.close()
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
-    rc, rc_n, t0, nt = shard_of_rank(rank, M, world, shard)
+    rc, rc_n, t0, nt = shard_of_rank(rank, M, world, shard, packed.num_classes)
     eng = Engine(class_shard(packed, rc, rc_n) if rc_n > 1 else packed, iouv=iouv, device=device)
     try:
         sub = None if ens_matrix is None else ens_matrix[t0:t0 + nt]

@@ -83,8 +83,8 @@ def test_shard_plan_and_class_partition():
     sys.path.insert(0, ROOT)
     import orie_b200  # noqa: F401
     from orie_b200.engine import class_partition, class_shard, shard_plan, shard_range
-    assert shard_plan(5000, 8) == (8, 1) and shard_plan(5000, 1) == (1, 1)            # COCO scale: classes only
-    assert shard_plan(50000, 8) == (2, 4) and shard_plan(50000, 4) == (2, 2) and shard_plan(50000, 2) == (1, 2)
+    assert shard_plan(5000, 8) == (8, 1) and shard_plan(5000, 1) == (1, 1) and shard_plan(50000, 8) == (8, 1)
+    assert shard_plan(5000, 8, num_classes=4) == (4, 2) and shard_plan(5000, 6, num_classes=4) == (3, 2)
     assert shard_plan(50000, 8, "grid:4x2") == (4, 2) and shard_plan(5000, 8, "targets") == (1, 8)
     with pytest.raises(ValueError):
         shard_plan(5000, 8, "grid:3x2")

@@ -107,9 +107,9 @@ def test_shard_ranges_cover_the_targets_once():
 
 
 def test_shard_mode_follows_the_dataset_size():
-    assert engine.pick_shard(5000) == "classes" and engine.pick_shard(28000) == "classes"
-    assert engine.pick_shard(50000) == "grid"
-    assert engine.shard_plan(5000, 8) == (8, 1) and engine.shard_plan(50000, 8) == (2, 4)
+    assert engine.pick_shard(5000) == "classes" and engine.pick_shard(50000) == "classes"
+    assert engine.shard_plan(5000, 8) == (8, 1) and engine.shard_plan(50000, 8) == (8, 1)
+    assert engine.shard_plan(5000, 8, num_classes=3) == (2, 4) and engine.shard_plan(5000, 8, num_classes=1) == (1, 8)
     assert engine.pick_shard(50000, "classes") == "classes" and engine.pick_shard(10, "targets") == "targets"
 
 
