@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kLayoutThreads) layout_kernel(const LayoutArgs
             const uint32_t cnt = live ? a.hist[st * a.C + c] : 0u;
             const uint32_t nch = live ? (cnt + (st == 0 ? 1u : 0u) + 31u) / 32u : 0u;
             const uint32_t segs = (nch + (uint32_t)a.seg_chunks - 1u) / (uint32_t)a.seg_chunks;
+            const uint32_t seglen = segs ? (nch + segs - 1u) / segs : 0u;     // equal-length segments: no short leftover
             uint32_t t_cnt, t_pad, t_seg;
             const uint32_t x_cnt = carry[st][0] + block_exclusive_scan<kLayoutThreads>(cnt, ws, &t_cnt);
             const uint32_t x_pad = carry[st][1] + block_exclusive_scan<kLayoutThreads>(nch * 32u, ws, &t_pad);
@@ -156,8 +157,8 @@ __global__ void __launch_bounds__(kLayoutThreads) layout_kernel(const LayoutArgs
                 const int64_t cap = st == 0 ? a.S_cap : a.SL_cap;
                 for (uint32_t k = 0; k < segs; ++k) {
                     if ((int64_t)(x_seg + k) >= cap) break;        // cannot happen: the capacities are upper bounds
-                    chunk0[x_seg + k] = (int32_t)(x_pad / 32u + k * (uint32_t)a.seg_chunks);
-                    len[x_seg + k] = (int32_t)min((uint32_t)a.seg_chunks, nch - k * (uint32_t)a.seg_chunks);
+                    chunk0[x_seg + k] = (int32_t)(x_pad / 32u + k * seglen);
+                    len[x_seg + k] = (int32_t)min(seglen, nch - k * seglen);
                 }
             }
         }
@@ -556,10 +557,12 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     // ---- capacities.  Detection stream: class c takes ceil((cnt_c + 1) / 32) <= cnt_c / 32 + 1 chunks; label stream:
     //      ceil(cnt_c / 32).  A class of nch chunks has ceil(nch / seg_chunks) <= nch / seg_chunks + 1 segments.
     const int64_t chunks_cap = Dw / 32 + C, chunksL_cap = G / 32 + C;
-    // Segment length: about two segments per average class (measured best for both the walk's load balance and the
-    // AP sweep on COCO-shaped data, profiles/), enough (batch, segment) warp items for >= 4 waves of 148 SMs x 8
-    // warps, and no segment so long that a single warp becomes the tail of the walk.  An event record keeps its rank
-    // inside the segment in 16 bits: at most 2047 chunks = 65504 slots per segment.
+    // Segment length: about two segments per average class — a class is cut into equal-length segments no longer
+    // than this (layout_kernel).  Measured on COCO- and VOC-shaped data (profiles/): shorter segments fill the walk's
+    // last wave of blocks better, but the AP sweep and the per-(batch, segment) query tables of the index pay per
+    // segment, and the sum is flat between two and three per class.  Enough (batch, segment) warp items for >= 4
+    // waves of 148 SMs x 8 warps, and no segment so long that a single warp becomes the tail of the walk.  An event
+    // record keeps its rank inside the segment in 16 bits: at most 2047 chunks = 65504 slots per segment.
     const int64_t seg_target = std::max<int64_t>(2 * C, ceil_div(4 * 148 * 8, ix->nbatch));
     const int seg_chunks = tune.seg_chunks > 0 ? std::min(tune.seg_chunks, 2047)
                                                : (int)std::min<int64_t>(512, std::max<int64_t>(16, ceil_div(chunks_cap, seg_target)));

@@ -16,7 +16,7 @@ dev = torch.device("cuda:0")
 dp = DevicePacked(HostPacked(pk), dev)
 torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-variants = [dict(), dict(ap_mode=1)]
+variants = [dict(seg_chunks=c) for c in [int(x) for x in (sys.argv[2].split(',') if len(sys.argv) > 2 else ['0'])]]
 ref = None
 for tv in variants:
     rows, idx = [], []
@@ -35,4 +35,5 @@ for tv in variants:
             err = float(np.abs(r - ref).max())
         eng.close()
     med = {k: round(float(np.median([r[k] for r in rows[1:]])), 4) for k in rows[0]}
+    import time as _t
     print(json.dumps({"tuning": tv, "match_index_ms": round(float(np.median(idx[1:])), 4), **med, "max_diff_vs_default": err}), flush=True)
