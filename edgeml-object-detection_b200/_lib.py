@@ -15,7 +15,7 @@ _LIB = None
 c_i64p = C.c_void_p   # device pointers are passed as plain addresses
 SYMBOLS = [
     "orie_last_error", "orie_version", "orie_match", "orie_dcsb",
-    "orie_index_build", "orie_index_sizes", "orie_index_build_into", "orie_index_destroy", "orie_index_info", "orie_index_status",
+    "orie_index_build", "orie_index_sizes", "orie_index_build_into", "orie_index_destroy", "orie_index_set_aux_stream", "orie_index_info", "orie_index_status",
     "orie_ensemble_from_indices", "orie_ensemble_sample", "orie_ensemble_sample_dev",
     "orie_reward_workspace_bytes", "orie_reward_workspace_bound", "orie_reward", "orie_reward_sums", "orie_rewards_from_sums",
     "orie_reward_profile", "orie_reward_depths", "orie_launch_count",
@@ -83,6 +83,8 @@ def load():
                                           vp, C.c_size_t, vp, C.c_size_t, vp, vp, C.POINTER(vp)]
     lib.orie_ensemble_sample_dev.restype = C.c_int
     lib.orie_ensemble_sample_dev.argtypes = [vp, i64, i64, i64, vp, vp, vp]
+    lib.orie_index_set_aux_stream.restype = C.c_int
+    lib.orie_index_set_aux_stream.argtypes = [vp, vp]
     lib.orie_index_status.restype = C.c_int
     lib.orie_index_status.argtypes = [vp]
     lib.orie_reward_workspace_bound.restype = C.c_size_t

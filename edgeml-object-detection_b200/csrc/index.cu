@@ -871,7 +871,22 @@ extern "C" int orie_index_build_into(int64_t M, int64_t C, int T, int64_t num_we
 extern "C" void orie_index_destroy(orie_index_t *ix) {
     if (!ix) return;
     for (int i = 0; i < ix->n_allocs; ++i) cudaFreeAsync(ix->allocs[i], ix->stream);
+    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
+    if (ix->ev_join) cudaEventDestroy(ix->ev_join);
     delete ix;
+}
+
+extern "C" int orie_index_set_aux_stream(orie_index_t *ix, orie_stream_t aux) {
+    if (!ix) {
+        set_error("orie_index_set_aux_stream: index is NULL");
+        return ORIE_EINVAL;
+    }
+    if (aux && !ix->ev_fork) {
+        ORIE_CUDA(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
+        ORIE_CUDA(cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming));
+    }
+    ix->aux = aux;
+    return ORIE_OK;
 }
 
 extern "C" int orie_index_status(const orie_index_t *ix) {

@@ -80,6 +80,10 @@ struct orie_index {
 
     int64_t device_bytes = 0;
     cudaStream_t stream = nullptr;   // stream the index was built on; its memory is freed on it
+    // optional auxiliary stream (orie_index_set_aux_stream): the reward pass runs its label walk there, next to the
+    // detection walk
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void *allocs[8] = {};
     int n_allocs = 0;
 };

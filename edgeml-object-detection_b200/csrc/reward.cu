@@ -928,7 +928,9 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         membership_table_kernel<<<grid, 256, 0, stream>>>(wp);
         ORIE_LAUNCH_CHECK();
     }
-    // labels
+    // labels: a small grid — on the auxiliary stream, if the caller gave one, it runs next to the detection walk
+    // (and fills its last, partly empty wave of blocks); not when per-kernel durations are being measured
+    const bool side = ix->aux != nullptr && ix->aux != stream && !marks;
     if (SL_grid > 0) {
         WalkParams lp = wp;
         lp.slot_img = ix->lab_slot_img; lp.seg_chunk0 = ix->lseg_chunk0; lp.seg_nch = ix->lseg_nch;
@@ -936,8 +938,15 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         lp.tot = (uint32_t *)(ws + L.totL);
         const unsigned ny = (unsigned)ceil_div(SL_grid, lp.segs_per_block);
         dim3 grid = gmem ? dim3(ny, (unsigned)nb) : dim3((unsigned)nb, ny);
-        ORIE_TRY(launch_walk<false>(grid, walk_threads, smem, gmem, stream, lp));
+        cudaStream_t ls = stream;
+        if (side) {
+            ORIE_CUDA(cudaEventRecord(ix->ev_fork, stream));
+            ORIE_CUDA(cudaStreamWaitEvent(ix->aux, ix->ev_fork, 0));
+            ls = ix->aux;
+        }
+        ORIE_TRY(launch_walk<false>(grid, walk_threads, smem, gmem, ls, lp));
         ORIE_LAUNCH_CHECK();
+        if (side) ORIE_CUDA(cudaEventRecord(ix->ev_join, ix->aux));
     }
     if (marks) ORIE_CUDA(cudaEventRecord(marks[1], stream));
     // detections
@@ -957,6 +966,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         ORIE_TRY(launch_walk<true>(grid, walk_threads, smem, gmem, stream, wp));
         ORIE_LAUNCH_CHECK();
     }
+    if (side && SL_grid > 0) ORIE_CUDA(cudaStreamWaitEvent(stream, ix->ev_join, 0));
     if (marks) ORIE_CUDA(cudaEventRecord(marks[2], stream));
     // AP
     ApParams ap;

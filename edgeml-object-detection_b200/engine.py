@@ -94,7 +94,8 @@ def shard_plan(num_images: int, world: int, shard: str = "auto", num_classes=Non
     """(class groups Rc, target blocks Rt), Rc * Rt == world.  Rank r works on the classes of group ``r % Rc`` (every
     image, only the rows of those classes: upload, matching, index build, walk and AP all shrink) and on the targets
     of block ``r // Rc`` (``shard_range``).  Per-target AP sums are additive over classes, so ONE all-reduce of a
-    zero-padded f64[M, 3] tensor combines every decomposition (``combine_sums``).
+    zero-padded f64[M, 3] tensor combines every decomposition (``combine_sums``; a rank that covers all targets hands
+    its tensor to the all-reduce as it is, which overwrites it with the totals).
     ``classes`` (= ``auto``) = (world, 1) — with fewer classes than ranks, the largest divisor of the world size that
     the classes can fill, the rest going to target blocks; ``targets`` = (1, world); ``grid:AxB`` = (A, B)."""
     world = int(world)
@@ -127,8 +128,11 @@ def combine_sums(local_sums, t0: int, num_images: int, T: int, n_used: int, grou
     target block in a zero tensor f64[M, 3]; one all-reduce adds the class groups and assembles the target blocks; the
     rewards follow from the sums (``rewards_from_sums``).  Works on CUDA tensors (NCCL) and on CPU tensors (gloo)."""
     import torch.distributed as dist
-    full = torch.zeros((num_images, 3), dtype=torch.float64, device=local_sums.device)
-    full[t0:t0 + local_sums.shape[0]] = local_sums
+    if t0 == 0 and local_sums.shape[0] == num_images and local_sums.is_contiguous():
+        full = local_sums                       # every rank covers all targets (class groups only): reduced in place
+    else:
+        full = torch.zeros((num_images, 3), dtype=torch.float64, device=local_sums.device)
+        full[t0:t0 + local_sums.shape[0]] = local_sums
     dist.all_reduce(full, group=group)
     return rewards_from_sums(full, T, n_used)
 
@@ -217,6 +221,9 @@ class Engine:
         self.ens_words = (self.M + 1 + 31) // 32
         with torch.cuda.device(self.device):
             self.stream = stream or torch.cuda.current_stream()
+            # where side work may start: the ensemble draw does not depend on the dataset and runs next to the index build
+            self._ev_start = torch.cuda.Event()
+            self._ev_start.record(self.stream)
             with torch.cuda.stream(self.stream):
                 if isinstance(packed, DevicePacked):
                     # matching runs on a side stream while the index build sorts by (class, confidence)
@@ -317,12 +324,16 @@ class Engine:
         index_bytes, temp_bytes = _INDEX_SIZES[key]
         self._index_mem = torch.empty(index_bytes, dtype=torch.uint8, device=self.device)
         temp = torch.empty(temp_bytes, dtype=torch.uint8, device=self.device)
-        self._temp_mem = temp if self._capturing else None      # a graph replays the build: its temporaries stay alive with it
+        # kept until the early ensemble draw (another stream) has been ordered behind the build — its buffers must not be
+        # carved out of these temporaries — and for good while a graph is being recorded (it replays the build)
+        self._temp_mem = temp
         _lib.check(self.lib.orie_index_build_into(
             self.M, self.Cn, self.T, self.Dw, self.Ds, self.G, _ptr(self.w_off), _ptr(self.w_cls), _ptr(self.w_conf), _ptr(self.w_tp),
             _ptr(self.s_off), _ptr(self.s_cls), _ptr(self.s_conf), _ptr(self.s_tp), _ptr(self.l_off), _ptr(self.l_cls),
             C.byref(self._tuning), _ptr(self._index_mem), index_bytes, _ptr(temp), temp_bytes, ev, self._s(), C.byref(h)))
         self._handle = h
+        self._aux = _side_streams(self.device)[0]
+        _lib.check(self.lib.orie_index_set_aux_stream(h, C.c_void_p(self._aux.cuda_stream)))
 
     @property
     def info(self):
@@ -342,6 +353,7 @@ class Engine:
         if self._handle:
             self.lib.orie_index_destroy(self._handle)
             self._handle = C.c_void_p(0)
+        self._temp_mem = None
 
     def __del__(self):
         try:
@@ -409,11 +421,30 @@ class Engine:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def _sample(self, t0, n, N, seed, seed_tensor, bits):
+    def _sample(self, t0, n, N, seed, seed_tensor, bits, early=False):
+        """Device-side ensemble draw.  ``early``: on the auxiliary stream, ordered behind the START of this engine's
+        setup only — the draw needs nothing from the dataset, so it runs next to the matching / index build; the main
+        stream waits for it before the walk."""
+        st, ev = self.stream, None
+        if early and self._ev_start is not None:
+            st = self._aux
+            st.wait_event(self._ev_start)
+            if not self._capturing:
+                bits.record_stream(st)
+                if seed_tensor is not None:
+                    seed_tensor.record_stream(st)
+        s = C.c_void_p(st.cuda_stream)
         if seed_tensor is not None:
-            _lib.check(self.lib.orie_ensemble_sample_dev(self._handle, t0, n, N, _ptr(seed_tensor), _ptr(bits), self._s()))
+            _lib.check(self.lib.orie_ensemble_sample_dev(self._handle, t0, n, N, _ptr(seed_tensor), _ptr(bits), s))
         else:
-            _lib.check(self.lib.orie_ensemble_sample(self._handle, t0, n, N, int(seed) & (2**64 - 1), _ptr(bits), self._s()))
+            _lib.check(self.lib.orie_ensemble_sample(self._handle, t0, n, N, int(seed) & (2**64 - 1), _ptr(bits), s))
+        if st is not self.stream:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self.stream.wait_event(ev)
+        self._ev_start = None          # one early draw per engine: later draws reuse buffers the walk may still read
+        if not self._capturing:
+            self._temp_mem = None      # everything enqueued from here on is ordered behind the build
 
     def orie_device(self, num_ensemble: int, ens_matrix=None, seed: int = 0, t0: int = 0, nt: int | None = None,
                     workspace_budget: int = 8 << 30, detail: bool = False, seed_tensor=None):
@@ -448,7 +479,7 @@ class Engine:
                     _lib.check(self.lib.orie_ensemble_from_indices(self._handle, t0 + a, n, _ptr(em[a:a + n]), N,
                                                                    _ptr(bits), _ptr(status), self._s()))
                 else:
-                    self._sample(t0 + a, n, N, seed, seed_tensor, bits)
+                    self._sample(t0 + a, n, N, seed, seed_tensor, bits, early=(a == 0))
                 _lib.check(self.lib.orie_reward(self._handle, t0 + a, n, _ptr(bits), N, _ptr(ws), ws.numel(),
                                                 _ptr(reward[a:]), _ptr(det[a:]) if detail else C.c_void_p(0), self._s()))
             self._status = status
@@ -506,7 +537,7 @@ class Engine:
                     _lib.check(self.lib.orie_ensemble_from_indices(self._handle, t0 + a, n, _ptr(em[a:a + n]), N,
                                                                    _ptr(bits), _ptr(status), self._s()))
                 else:
-                    self._sample(t0 + a, n, N, seed, seed_tensor, bits)
+                    self._sample(t0 + a, n, N, seed, seed_tensor, bits, early=(a == 0))
                 _lib.check(self.lib.orie_reward_sums(self._handle, t0 + a, n, _ptr(bits), N, _ptr(ws), ws.numel(),
                                                      _ptr(sums[a:]), 1 if full else 0, self._s()))
             self._status = status

@@ -150,6 +150,9 @@ int orie_index_build_into(int64_t M, int64_t C, int T,
                           void *index_mem, size_t index_bytes, void *temp_mem, size_t temp_bytes, /* 256-byte aligned */
                           orie_event_t tp_ready /* nullable */, orie_stream_t stream, orie_index_t **out);
 void orie_index_destroy(orie_index_t *idx);
+/* Optional: an auxiliary stream the reward pass may use for the kernels that can run side by side (the label walk
+ * next to the detection walk); ordering with the main stream is kept with events inside the call.  NULL = none. */
+int orie_index_set_aux_stream(orie_index_t *idx, orie_stream_t aux);
 /* Waits for the build (first call only), then reports the exact sizes; returns the build's error code if the device
  * rejected the input (ORIE_EDATA: class id outside [0, C) or offsets inconsistent with the row counts; ORIE_ELIMIT:
  * more than 65535 rows in one image file). */
