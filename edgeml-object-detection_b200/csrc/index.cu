@@ -200,8 +200,8 @@ struct PostArgs {
     const uint32_t *cls_off, *pad_off, *lcls_off, *lpad_off;
     const int64_t *w_off, *s_off;
     uint32_t *lcursor;
-    uint32_t *slot_img, *lab_slot_img;
-    uint16_t *slot_tp;
+    uint32_t *slot_img, *lab_slot_img, *slot_pk, *ev_img;
+    uint16_t *slot_tp, *ev_mask;
     uint32_t *q_of_det, *pos_of_det, *ownpos;
     uint32_t *own_w_q, *own_s_q;
     uint16_t *own_w_m, *own_s_m, *own_w_c, *own_s_c, *own_w_cs, *own_s_cs;
@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
         if (slot < a.pad_off[c + 1]) {
             a.slot_img[slot] = (uint32_t)a.M;
             a.slot_tp[slot] = 0;
+            if (a.slot_pk) a.slot_pk[slot] = (uint32_t)a.M;
         }
         const uint32_t lslot = a.lpad_off[c] + (a.lcls_off[c + 1] - a.lcls_off[c]) + (uint32_t)i;
         if (lslot < a.lpad_off[c + 1]) a.lab_slot_img[lslot] = (uint32_t)a.M;
@@ -248,8 +249,11 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
         a.q_of_det[u] = slot;       // weak: its own slot; strong: the slot it would be inserted in front of
         a.pos_of_det[u] = (uint32_t)v;
         if (u < a.d.Dw) {
-            a.slot_img[slot] = a.img_all[u];
-            a.slot_tp[slot] = a.d.w_tp[u];
+            const uint32_t im = a.img_all[u];
+            const uint16_t tp = a.d.w_tp[u];
+            a.slot_img[slot] = im;
+            a.slot_tp[slot] = tp;
+            if (a.slot_pk) a.slot_pk[slot] = im | ((uint32_t)tp << 16);
         }
     }
     for (int64_t g = gtid; g < a.G; g += gsize) {
@@ -359,10 +363,19 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostArgs a) {
         uint32_t carry, grand;
         block_exclusive_scan<kPostThreads>(before, ws, &carry);
         block_exclusive_scan<kPostThreads>(all, ws, &grand);
-        if (blockIdx.x == 0 && threadIdx.x == 0) a.meta->Ev = grand;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            a.meta->Ev = grand;
+            a.seg_ev0[S] = grand;
+        }
         uint32_t run = carry + warp_base;
         for (int64_t ch = w0; ch < w1; ++ch) {
-            const unsigned b = __ballot_sync(kFull, __ldcg(a.slot_tp + ch * 32 + lane) != 0);
+            const uint16_t tp = __ldcg(a.slot_tp + ch * 32 + lane);
+            const unsigned b = __ballot_sync(kFull, tp != 0);
+            if (tp != 0) {                                 // the dense event stream, in slot order
+                const uint32_t at = run + __popc(b & ((1u << lane) - 1u));
+                a.ev_img[at] = __ldcg(a.slot_img + ch * 32 + lane);
+                a.ev_mask[at] = tp;
+            }
             if (lane == 0) {
                 __stcg(a.evbase + ch, run);
                 int64_t lo = 0, hi = S;                    // is this chunk the first of a segment?
@@ -591,9 +604,13 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&ix->gtcnt, M * C);
     A.add(&ix->slot_img, ix->P_cap);
     A.add(&ix->slot_tp, ix->P_cap);
+    const bool packed = M <= 65535 && !tune.walk_unpacked;     // image and mask of a slot fit one 32-bit word
+    if (packed) A.add(&ix->slot_pk, ix->P_cap);
+    A.add(&ix->ev_img, ix->Ev_cap);
+    A.add(&ix->ev_mask, ix->Ev_cap);
     A.add(&ix->seg_chunk0, ix->S_cap);
     A.add(&ix->seg_nch, ix->S_cap);
-    A.add(&ix->seg_ev0, ix->S_cap);
+    A.add(&ix->seg_ev0, ix->S_cap + 1);
     A.add(&ix->cls_seg0, C + 1);
     A.add(&ix->cls_order, C);
     A.add(&ix->bqoff, ix->nbatch * (ix->S_cap + 1));
@@ -733,6 +750,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
         pa.w_off = ix->w_off; pa.s_off = ix->s_off;
         pa.lcursor = lcursor;
         pa.slot_img = ix->slot_img; pa.lab_slot_img = ix->lab_slot_img; pa.slot_tp = ix->slot_tp;
+        pa.slot_pk = ix->slot_pk; pa.ev_img = ix->ev_img; pa.ev_mask = ix->ev_mask;
         pa.q_of_det = q_of_det; pa.pos_of_det = pos_of_det; pa.ownpos = ownpos;
         pa.own_w_q = ix->own_w_q; pa.own_s_q = ix->own_s_q; pa.own_w_m = ix->own_w_m; pa.own_s_m = ix->own_s_m;
         pa.own_w_c = own_w_c; pa.own_s_c = own_s_c; pa.own_w_cs = ix->own_w_cs; pa.own_s_cs = ix->own_s_cs;

@@ -44,9 +44,12 @@ struct orie_index {
     //      to a whole number of 32-slot chunks with at least one padding slot
     uint32_t *slot_img = nullptr;    // [P_cap] image of the detection in the slot (M for padding)
     uint16_t *slot_tp = nullptr;     // [P_cap] its true-positive mask (0 for padding); non-zero = "event"
+    uint32_t *slot_pk = nullptr;     // [P_cap] image | mask << 16: one load per slot for the walk; only with M <= 65535
+    uint32_t *ev_img = nullptr;      // [Ev_cap] dense event stream: image ...
+    uint16_t *ev_mask = nullptr;     // [Ev_cap] ... and true-positive mask of the slots that hold an event, in slot order
     int32_t *seg_chunk0 = nullptr;   // [S_cap]
     int32_t *seg_nch = nullptr;      // [S_cap]
-    uint32_t *seg_ev0 = nullptr;     // [S_cap] events in front of the segment
+    uint32_t *seg_ev0 = nullptr;     // [S_cap + 1] events in front of the segment; [S] = all events
     int32_t *cls_seg0 = nullptr;     // [C+1]
     int32_t *cls_order = nullptr;    // [C] classes by descending weak-detection count
 

@@ -181,12 +181,17 @@ struct WalkParams {
     uint32_t *tot;              // [S][ntp]
     // detection stream only
     const uint16_t *slot_tp;
-    const uint32_t *seg_ev0;
+    const uint32_t *slot_pk;    // image | true-positive mask << 16 (PACKED kernels: at most 65535 images)
+    const uint32_t *seg_ev0;    // [S + 1]
+    const uint32_t *ev_img;     // dense event stream (the slots holding a true positive, in slot order): image ...
+    const uint16_t *ev_mask;    // ... and true-positive mask
     const uint2 *bq;            // per-batch query list (both detectors), ascending by slot
     const uint32_t *bqoff;      // [nbatch][S_cap+1]
     int64_t Ev;                 // capacity of one target's event list in the workspace (>= the index's event count)
+    int T;
     uint32_t *evcnt;            // [S][ntp]
     uint32_t *ev;               // [ntp][Ev] event records: rank inside the segment (16 bits) | TP mask << 16
+    uint16_t *kseg;             // [S][T][ntp] member true positives of the segment per IoU threshold
     uint32_t *cb_w, *cb_s;
 };
 
@@ -209,9 +214,20 @@ __global__ void membership_table_kernel(const WalkParams p) {
 // THREADS is the block size the kernel is launched with (256 / 512 / 1024, chosen from the size of the
 // membership table); the register cap keeps kWalkResident threads resident per SM (at 1536 the compiler
 // re-materialised the transposer's per-lane constants inside the chunk loop: 13 % more instructions).  GMEM: the membership table was
-// built by membership_table_kernel and is read through L1 instead of shared memory.
-constexpr int kWalkResident = 1280;
-template <bool DETS, int THREADS, bool GMEM>
+// built by membership_table_kernel and is read through L1 instead of shared memory.  PACKED (at most 65535 images):
+// one 32-bit load per slot brings the image and the true-positive mask.
+//
+// Per segment and 32 targets a warp runs two loops:
+//  * the slot loop, two chunks per trip so that two table lookups + bit transposes are in flight: running member
+//    counts, an event record for every member true positive, the rank of the batch's own detections;
+//  * a short dense loop over the segment's events only (32 per trip): members that are true positives at each IoU
+//    threshold (one ballot per threshold) — the count the AP sweep starts from, which it would otherwise have to
+//    collect by reading every event record of the class.
+#ifndef ORIE_WALK_RESIDENT
+#define ORIE_WALK_RESIDENT 1280
+#endif
+constexpr int kWalkResident = ORIE_WALK_RESIDENT;
+template <bool DETS, int THREADS, bool GMEM, bool PACKED>
 __global__ void __launch_bounds__(THREADS, kWalkResident / THREADS > 0 ? kWalkResident / THREADS : 1)
 walk_kernel(const WalkParams p) {
     extern __shared__ uint32_t memb_s[];   // [ens_words * 32]: bit j of memb[img] = img in ensemble of target 32*batch+j
@@ -243,57 +259,115 @@ walk_kernel(const WalkParams p) {
         }
         __syncthreads();
     }
+    // table lookup: membership word of an image (bit j: member of the ensemble of target 32*batch+j); image M, the
+    // sentinel of padding slots, is a member of nothing.  The shared-memory window address is computed once.
+    uint32_t memb_sa = 0u;
+    if (!GMEM)        // through an opaque move: otherwise the window base is re-derived in every trip of the slot loop
+        asm volatile("mov.u32 %0, %1;" : "=r"(memb_sa) : "r"((uint32_t)__cvta_generic_to_shared(memb_s)));
+    auto lookup = [&](uint32_t img) -> uint32_t {
+        if (GMEM) return __ldg(memb + img);
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(memb_sa + img * 4u));
+        return v;
+    };
+    const uint32_t sentinel = (uint32_t)p.M;       // image M with an empty mask
     const int64_t gb = (p.t0 >> 5) + lb;           // global batch (query lists are per global batch)
     const int64_t sbeg = yb * p.segs_per_block;
     const int64_t send = min(sbeg + p.segs_per_block, S);
     for (int64_t s = sbeg + warp; s < send; s += kWarps) {
         const int64_t ch0 = p.seg_chunk0[s];
         const int nch = p.seg_nch[s];
-        uint32_t cnt = 0, ecur = 0;
+        uint32_t cnt = 0;
         uint32_t qi = 0, q_end = 0;
-        uint2 nq = make_uint2(0xffffffffu, 0u);
+        uint2 nq = make_uint2(0u, 0u);
+        int nqc = 0x7fffffff;                      // chunk (relative to the segment) of the next own detection
         uint32_t *evout = nullptr;
+        uint32_t ecur = 0;
         if (DETS) {
             evout = p.ev + tl * p.Ev + p.seg_ev0[s];
+            asm volatile("" : "+l"(evout));        // kept in registers: otherwise re-derived for every record written
             const uint32_t *o = p.bqoff + gb * (p.S_cap + 1) + s;
             qi = o[0]; q_end = o[1];
-            if (qi < q_end) nq = p.bq[qi];
-        }
-        const uint32_t *simg = p.slot_img + ch0 * 32 + lane;
-        const uint16_t *stp = DETS ? p.slot_tp + ch0 * 32 + lane : nullptr;
-        uint32_t img_next = simg[0];               // software pipeline: the next chunk's images and masks are in flight
-        uint32_t tp_next = DETS ? (uint32_t)stp[0] : 0u;
-        for (int c = 0; c < nch; ++c) {
-            const uint32_t img = img_next;
-            const uint32_t tp = tp_next;           // true-positive mask of MY slot of the chunk
-            if (c + 1 < nch) {
-                img_next = simg[(int64_t)(c + 1) * 32];
-                if (DETS) tp_next = stp[(int64_t)(c + 1) * 32];
+            if (qi < q_end) {
+                nq = p.bq[qi];
+                nqc = (int)(((nq.x & 0x7fffffffu) >> 5) - (uint32_t)ch0);
             }
-            const uint32_t word = transpose(GMEM ? __ldg(memb + img) : memb[img]);   // bit l: slot l holds a member of MY target
+        }
+        // one chunk: `x` = image of MY slot (PACKED: | TP mask << 16), `tpv` = TP mask of MY slot << 16 (PACKED: x itself,
+        // the image bits below are ignored), `word` bit l: slot l holds a member of MY target
+        auto chunk = [&](const uint32_t tpv, const uint32_t word, const int c) {
             if (DETS) {
-                uint32_t eb = __ballot_sync(kFull, tp != 0u);       // slots of the chunk holding an event
+                uint32_t eb = __ballot_sync(kFull, tpv >= 0x10000u);    // slots of the chunk holding an event
                 while (eb) {
                     const int b = __ffs(eb) - 1;
                     eb &= eb - 1;
-                    const uint32_t mask = __shfl_sync(kFull, tp, b);
-                    if ((word >> b) & 1u) {
-                        const uint32_t rank = cnt + __popc(word & ((2u << b) - 1u));   // 1-based, inclusive
-                        evout[ecur++] = rank | (mask << 16);        // rank <= 65504 slots per segment (index.cu)
-                    }
+                    const uint32_t m = __shfl_sync(kFull, tpv, b);
+                    const uint32_t sh = word << (31 - b);               // slot b on top, the slots behind it shifted out
+                    if ((int)sh < 0) evout[ecur++] = (cnt + __popc(sh)) | (m & 0xffff0000u);   // 1-based rank <= 65504 (index.cu)
                 }
-                const uint32_t chunk_end = (uint32_t)(ch0 + c + 1) * 32u;
-                while ((nq.x & 0x7fffffffu) < chunk_end) {       // uniform: own detections (weak: sitting, strong: inserted) in this chunk
+                while (nqc <= c) {       // uniform: own detections (weak: sitting, strong: inserted) in this chunk
                     if (lane == (int)(nq.y >> 27))
                         ((nq.x >> 31) ? p.cb_s : p.cb_w)[nq.y & 0x07ffffffu] = cnt + __popc(word & ((1u << (nq.x & 31u)) - 1u));
                     ++qi;
-                    nq = qi < q_end ? p.bq[qi] : make_uint2(0xffffffffu, 0u);
+                    nqc = 0x7fffffff;
+                    if (qi < q_end) {
+                        nq = p.bq[qi];
+                        nqc = (int)(((nq.x & 0x7fffffffu) >> 5) - (uint32_t)ch0);
+                    }
                 }
             }
             cnt += __popc(word);
+        };
+        const uint32_t *sp = ((DETS && PACKED) ? p.slot_pk : p.slot_img) + ch0 * 32 + lane;
+        const uint16_t *stp = (DETS && !PACKED) ? p.slot_tp + ch0 * 32 + lane : nullptr;
+        // software pipeline: the next two chunks' slots are in flight while two are being worked on; a segment with an
+        // odd number of chunks ends with a chunk of sentinels
+        uint32_t x0 = sp[0], x1 = nch > 1 ? sp[32] : sentinel;
+        uint32_t t0 = 0u, t1 = 0u;
+        if (DETS && !PACKED) { t0 = stp[0]; t1 = nch > 1 ? (uint32_t)stp[32] : 0u; }
+        for (int c = 0; c < nch; c += 2) {
+            const uint32_t a = x0, b = x1, ta = t0, tb = t1;
+            sp += 64;
+            if (c + 2 < nch) x0 = sp[0];
+            x1 = c + 3 < nch ? sp[32] : sentinel;
+            if (DETS && !PACKED) {
+                stp += 64;
+                if (c + 2 < nch) t0 = stp[0];
+                t1 = c + 3 < nch ? (uint32_t)stp[32] : 0u;
+            }
+            const uint32_t wa = transpose(lookup(PACKED && DETS ? a & 0xffffu : a));
+            const uint32_t wb = transpose(lookup(PACKED && DETS ? b & 0xffffu : b));
+            chunk(PACKED ? a : ta << 16, wa, c);
+            chunk(PACKED ? b : tb << 16, wb, c + 1);
         }
         p.tot[s * p.ntp + tl] = cnt;
-        if (DETS) p.evcnt[s * p.ntp + tl] = ecur;
+        if (DETS) {
+            p.evcnt[s * p.ntp + tl] = ecur;
+            // member true positives per threshold: 32 events per trip, counts of two thresholds share a register
+            // (a segment has at most 65504 slots)
+            const uint32_t e0 = p.seg_ev0[s], e1 = p.seg_ev0[s + 1];
+            uint32_t kc[ORIE_MAX_THRESHOLDS / 2];
+#pragma unroll
+            for (int i = 0; i < ORIE_MAX_THRESHOLDS / 2; ++i) kc[i] = 0u;
+            for (uint32_t w0 = e0 & ~31u; w0 < e1; w0 += 32u) {
+                const uint32_t e = w0 + lane;
+                const bool in = e >= e0 && e < e1;
+                const uint32_t img = in ? p.ev_img[e] : sentinel;
+                const uint32_t mask = in ? (uint32_t)p.ev_mask[e] : 0u;
+                const uint32_t word = transpose(lookup(img));
+#pragma unroll
+                for (int t = 0; t < ORIE_MAX_THRESHOLDS; ++t) {
+                    if (t < p.T) {          // uniform
+                        const uint32_t tb = __ballot_sync(kFull, (mask >> t) & 1u);
+                        kc[t >> 1] += (uint32_t)__popc(word & tb) << ((t & 1) * 16);
+                    }
+                }
+            }
+            uint16_t *ko = p.kseg + (s * p.T) * p.ntp + tl;
+#pragma unroll
+            for (int t = 0; t < ORIE_MAX_THRESHOLDS; ++t)
+                if (t < p.T) ko[(int64_t)t * p.ntp] = (uint16_t)(kc[t >> 1] >> ((t & 1) * 16));
+        }
     }
 }
 
@@ -317,6 +391,7 @@ struct ApParams {
     const uint32_t *nact;       // [M]
     const uint32_t *seg_ev0;
     const uint32_t *tot, *evcnt, *totL;
+    const uint16_t *kseg;       // [S][T][ntp] member true positives per segment and threshold (walk_kernel)
     const uint32_t *ev;
     const uint32_t *gtcnt;
     const int64_t *w_off, *s_off;
@@ -355,11 +430,11 @@ struct ApVar {
     int g;                // highest grid point not yet integrated
     bool dead;
 
-    // ge[4] == 1 (set by the host when every bit of the tie table is set, which holds for np.linspace's grid):
-    // an exact tie always counts as "reached" and the table lookup is skipped
+    // ge == nullptr (the kernel passes that when every bit of the tie table is set — Grid101::ge[4], which holds for
+    // np.linspace's grid): an exact tie always counts as "reached" and the table lookup is skipped
     __device__ __forceinline__ int first_grid(const uint32_t *ge) const {
         int gl = q + (r > 0);
-        if (!ge[4] && r == 0 && gl <= 100 && !((ge[gl >> 5] >> (gl & 31)) & 1u)) ++gl;
+        if (ge != nullptr && r == 0 && gl <= 100 && !((ge[gl >> 5] >> (gl & 31)) & 1u)) ++gl;
         return gl;
     }
     __device__ __forceinline__ void init(const double *cw, const double *cwx, const uint32_t *ge, uint32_t K, uint32_t n_p,
@@ -434,6 +509,9 @@ struct OwnCursor {
 };
 
 constexpr int kApThreads = 128;
+#ifndef ORIE_AP_BLOCKS
+#define ORIE_AP_BLOCKS 8
+#endif
 
 // One warp per (target, group of 32/T classes); lane = (class slot, IoU threshold).
 //
@@ -450,21 +528,20 @@ constexpr int kApThreads = 128;
 //
 // The number of ground-truth classes (the mean's denominator, lib/metrics.py:104-107) is counted separately, lane =
 // class, by the first ceil(C / 32) warps of the target.  The number of member true positives of a class at every
-// threshold (K, where the reverse sweep starts) is counted by the whole warp: 32 event records per step, one ballot
-// per threshold.
-// MODE bits (orie_tuning_t::ap_mode selects among the instantiations): 1 = member true positives counted by the whole
-// warp (32 records per step, one ballot per threshold) instead of per lane; 2 = the warp's classes come from the
-// image's active-class list instead of fixed cls_order groups.
+// threshold (K, where the reverse sweep starts) comes from the walk (kseg).
+// MODE (orie_tuning_t::ap_mode selects among the instantiations): 2 = the warp's classes come from the image's
+// active-class list (default), 0 = fixed cls_order groups.
 template <bool FULL, int MODE, bool DEPTHS = false>
-__global__ void __launch_bounds__(kApThreads, 8)
+__global__ void __launch_bounds__(kApThreads, ORIE_AP_BLOCKS)
 ap_kernel(const ApParams p, const Grid101 grid) {
     __shared__ double cw[102];
     __shared__ double cwx[102];
-    __shared__ uint32_t ge[5];
+    __shared__ uint32_t ge_s[5];
     if (p.meta->status) return;                 // uniform: rejected input or a workspace flagged too small by the walk
     for (int i = threadIdx.x; i < 102; i += kApThreads) { cw[i] = grid.cw[i]; cwx[i] = grid.cwx[i]; }
-    if (threadIdx.x < 5) ge[threadIdx.x] = grid.ge[threadIdx.x];
+    if (threadIdx.x < 5) ge_s[threadIdx.x] = grid.ge[threadIdx.x];
     __syncthreads();
+    const uint32_t *ge = grid.ge[4] ? nullptr : ge_s;      // uniform
     const int lane = threadIdx.x & 31;
     const int64_t item = (int64_t)blockIdx.x * (kApThreads / 32) + (threadIdx.x >> 5);
     if (item >= p.nt * p.class_groups) return;
@@ -507,49 +584,16 @@ ap_kernel(const ApParams p, const Grid101 grid) {
         // the target has no detection of this class from either detector: both variants are the same integral
         const bool same = (wb == wa) && (sb == sa);
         const bool need = active && n_l > 0 && (FULL || !same);
-        // members of the class (n_ens) and member true positives at this lane's threshold (K_ens), by the whole warp
+        // members of the class (n_ens) and member true positives at this lane's threshold (K_ens): sums over the
+        // class's segments of what the walk counted
         uint32_t n_ens = 0, K_ens = 0;
-        const int nslots = (int)min((int64_t)p.cls_per_warp, nact - first);
-        if (!(MODE & 1)) {
-            if (need) {
-                const int s0 = p.cls_seg0[c], s1 = p.cls_seg0[c + 1];
-                for (int s = s0; s < s1; ++s) {
-                    n_ens += tot[(int64_t)s * p.ntp];
-                    const uint32_t *e = ev + p.seg_ev0[s];
-                    const int ne = (int)evcnt[(int64_t)s * p.ntp];
-                    int i = 0;
-                    for (; i + 4 <= ne; i += 4) {           // four independent loads in flight
-                        const uint32_t a = e[i], b = e[i + 1], c2 = e[i + 2], d = e[i + 3];
-                        K_ens += ((a >> (16 + t)) & 1u) + ((b >> (16 + t)) & 1u) + ((c2 >> (16 + t)) & 1u) + ((d >> (16 + t)) & 1u);
-                    }
-                    for (; i < ne; ++i) K_ens += (e[i] >> (16 + t)) & 1u;
-                }
-            }
-        } else
-        for (int sl = 0; sl < nslots; ++sl) {
-            const int src = sl * p.T;
-            if (!__shfl_sync(kFull, (int)need, src)) continue;             // uniform
-            const int cc = __shfl_sync(kFull, c, src);
-            const int s0 = p.cls_seg0[cc], s1 = p.cls_seg0[cc + 1];
-            uint32_t acc_n = 0, acc_k = 0;
-            for (int s = s0 + lane; s < s1; s += 32) acc_n += tot[(int64_t)s * p.ntp];
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) acc_n += __shfl_xor_sync(kFull, acc_n, d);
-            for (int s = s0; s < s1; ++s) {
-                const uint32_t *e = ev + p.seg_ev0[s];
-                const int ne = (int)evcnt[(int64_t)s * p.ntp];
-                for (int i0 = 0; i0 < ne; i0 += 32) {
-                    const uint32_t rec = i0 + lane < ne ? e[i0 + lane] : 0u;
-                    for (int tt = 0; tt < p.T; ++tt) {
-                        const unsigned b = __ballot_sync(kFull, (rec >> (16 + tt)) & 1u);
-                        if (tt == t) acc_k += __popc(b);
-                    }
-                }
-            }
-            if (slot == sl) { n_ens = acc_n; K_ens = acc_k; }
-        }
         if (need) {
             const int s0 = p.cls_seg0[c], s1 = p.cls_seg0[c + 1];
+            const uint16_t *ks = p.kseg + tl + (int64_t)t * p.ntp;
+            for (int s = s0; s < s1; ++s) {
+                n_ens += tot[(int64_t)s * p.ntp];
+                K_ens += ks[(int64_t)s * p.T * p.ntp];
+            }
             const uint32_t *wq = p.own_w_q + p.w_off[j], *wcb = p.cb_w + p.w_off[j];
             const uint32_t *sq = p.own_s_q + p.s_off[j], *scb = p.cb_s + p.s_off[j];
             const uint16_t *wm = p.own_w_m + p.w_off[j], *sm = p.own_s_m + p.s_off[j];
@@ -700,7 +744,7 @@ __global__ void rewards_from_sums_kernel(const double *__restrict__ sums, int64_
 // whatever the caller's workspace has left (at least the index's event count, checked on the host once the exact
 // count is known, on the device otherwise).
 struct WsLayout {
-    size_t tot, evcnt, totL, cb_w, cb_s, partial, memb, ev, fixed;
+    size_t tot, evcnt, totL, kseg, cb_w, cb_s, partial, memb, ev, fixed;
 };
 
 static bool walk_in_gmem(const orie_index *ix) {
@@ -717,6 +761,7 @@ static WsLayout ws_layout(const orie_index *ix, int64_t nt) {
     L.tot = take(ix->S_cap * ntp * 4);
     L.evcnt = take(ix->S_cap * ntp * 4);
     L.totL = take(ix->SL_cap * ntp * 4);
+    L.kseg = take(ix->S_cap * ix->T * ntp * 2);
     L.cb_w = take(ix->Dw * 4);
     L.cb_s = take(ix->Ds * 4);
     L.partial = take(ntp * ix->class_groups * 3 * 8);
@@ -740,12 +785,15 @@ static int walk_attributes() {
     std::lock_guard<std::mutex> lock(mu);
     if (dev < 0 || dev >= 64 || done[dev]) return ORIE_OK;
     const int smem = 112 * 1024;
-    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 512, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 1024, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 512, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<true, 1024, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 512, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 1024, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     done[dev] = true;
     return ORIE_OK;
 }
@@ -827,17 +875,23 @@ extern "C" int orie_ensemble_sample_dev(const orie_index_t *ix, int64_t t0, int6
     return ensemble_sample(ix, t0, nt, N, 0, seed_dev, ens_bits, stream);
 }
 
-template <bool DETS, int THREADS, bool GMEM>
+template <bool DETS, int THREADS, bool GMEM, bool PACKED>
 static int launch_walk_t(dim3 grid, size_t smem, cudaStream_t stream, const WalkParams &p) {
-    walk_kernel<DETS, THREADS, GMEM><<<grid, THREADS, GMEM ? 0 : smem, stream>>>(p);
+    walk_kernel<DETS, THREADS, GMEM, PACKED><<<grid, THREADS, GMEM ? 0 : smem, stream>>>(p);
     return ORIE_OK;
 }
+template <bool DETS, bool PACKED>
+static int launch_walk_p(dim3 grid, int threads, size_t smem, bool gmem, cudaStream_t stream, const WalkParams &p) {
+    if (gmem) return launch_walk_t<DETS, 256, true, PACKED>(grid, smem, stream, p);
+    if (threads == 256) return launch_walk_t<DETS, 256, false, PACKED>(grid, smem, stream, p);
+    if (threads == 512) return launch_walk_t<DETS, 512, false, PACKED>(grid, smem, stream, p);
+    return launch_walk_t<DETS, 1024, false, PACKED>(grid, smem, stream, p);
+}
+// the label stream has no true-positive masks: never packed
 template <bool DETS>
 static int launch_walk(dim3 grid, int threads, size_t smem, bool gmem, cudaStream_t stream, const WalkParams &p) {
-    if (gmem) return launch_walk_t<DETS, 256, true>(grid, smem, stream, p);
-    if (threads == 256) return launch_walk_t<DETS, 256, false>(grid, smem, stream, p);
-    if (threads == 512) return launch_walk_t<DETS, 512, false>(grid, smem, stream, p);
-    return launch_walk_t<DETS, 1024, false>(grid, smem, stream, p);
+    if (DETS && p.slot_pk) return launch_walk_p<DETS, DETS>(grid, threads, smem, gmem, stream, p);
+    return launch_walk_p<DETS, false>(grid, threads, smem, gmem, stream, p);
 }
 
 // np.linspace(0, 1, 101) and the cumulative trapezoid weights of np.trapz over it, bit for bit
@@ -929,8 +983,10 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         ORIE_LAUNCH_CHECK();
     }
     // labels: a small grid — on the auxiliary stream, if the caller gave one, it runs next to the detection walk
-    // (and fills its last, partly empty wave of blocks); not when per-kernel durations are being measured
-    const bool side = ix->aux != nullptr && ix->aux != stream && !marks;
+    // (and fills its last, partly empty wave of blocks); not when per-kernel durations are being measured, and not
+    // with the membership tables in global memory: the detection walk's block order keeps the tables in flight
+    // L2-resident, and a second kernel walking them in another order evicts them (50k sweep: +17 ms)
+    const bool side = ix->aux != nullptr && ix->aux != stream && !marks && !gmem;
     if (SL_grid > 0) {
         WalkParams lp = wp;
         lp.slot_img = ix->lab_slot_img; lp.seg_chunk0 = ix->lseg_chunk0; lp.seg_nch = ix->lseg_nch;
@@ -954,7 +1010,9 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         wp.slot_img = ix->slot_img; wp.seg_chunk0 = ix->seg_chunk0; wp.seg_nch = ix->seg_nch;
         wp.segs_per_block = segs_per_block(S_grid);
         wp.tot = (uint32_t *)(ws + L.tot);
-        wp.slot_tp = ix->slot_tp; wp.seg_ev0 = ix->seg_ev0;
+        wp.slot_tp = ix->slot_tp; wp.slot_pk = ix->slot_pk; wp.seg_ev0 = ix->seg_ev0;
+        wp.ev_img = ix->ev_img; wp.ev_mask = ix->ev_mask; wp.T = ix->T;
+        wp.kseg = (uint16_t *)(ws + L.kseg);
         wp.bq = ix->bq; wp.bqoff = ix->bqoff;
         wp.Ev = ev_stride;
         wp.evcnt = (uint32_t *)(ws + L.evcnt);
@@ -978,6 +1036,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     ap.act_cls = ix->act_cls; ap.nact = ix->nact;
     ap.tot = (const uint32_t *)(ws + L.tot); ap.evcnt = (const uint32_t *)(ws + L.evcnt);
     ap.totL = (const uint32_t *)(ws + L.totL); ap.ev = (const uint32_t *)(ws + L.ev);
+    ap.kseg = (const uint16_t *)(ws + L.kseg);
     ap.gtcnt = ix->gtcnt; ap.w_off = ix->w_off; ap.s_off = ix->s_off;
     ap.own_w_cs = ix->own_w_cs; ap.own_s_cs = ix->own_s_cs; ap.own_w_m = ix->own_w_m; ap.own_s_m = ix->own_s_m;
     ap.own_w_q = ix->own_w_q; ap.own_s_q = ix->own_s_q;
@@ -989,7 +1048,6 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     if (depths) ap_kernel<false, 0, true><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());
     else if (full) ap_kernel<true, 0><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());
     else if (ix->ap_mode == 1) ap_kernel<false, 0><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());   // fixed cls_order groups
-    else if (ix->ap_mode == 3) ap_kernel<false, 3><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());
     else ap_kernel<false, 2><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());      // default: depth-ordered active classes
     ORIE_LAUNCH_CHECK();
     if (marks) ORIE_CUDA(cudaEventRecord(marks[3], stream));

@@ -124,6 +124,8 @@ typedef struct {
     int32_t walk_gmem;        /* != 0: keep the walk's membership tables in global memory even if they fit shared memory */
     int32_t ap_mode;          /* AP kernel variant (measurement knob, results identical up to summation order): 0 = default */
     int32_t sort_lsd;         /* != 0: sort the dataset with the LSD radix passes instead of the bucket sort */
+    int32_t walk_unpacked;    /* != 0: the walk reads image and true-positive mask of a slot from two arrays even when
+                               * they fit one 32-bit word (<= 65535 images), i.e. the path of larger datasets */
     double walk_waves;        /* resident-block waves the walk grid is sized for; 0 = default (2) */
 } orie_tuning_t;
 

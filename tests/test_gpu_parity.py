@@ -124,6 +124,21 @@ def test_global_memory_membership_table_matches():
     eng.close(); eng2.close()
 
 
+def test_unpacked_slot_stream_matches():
+    """Up to 65535 images the walk reads one 32-bit word per slot (image | TP mask << 16); larger datasets read the two
+    arrays.  Force the two-array path (shared- and global-memory table) on a small dataset: identical bits."""
+    M, N = 140, 60
+    _, pk = make_packed(M=M, seed=45)
+    eng = _engine(pk, O.IOU_05_095)
+    em = O.ensemble_matrix(M, N, 10)
+    ref = eng.orie(N, ens_matrix=em)
+    for tv in (dict(walk_unpacked=1), dict(walk_unpacked=1, walk_gmem=1)):
+        eng2 = _engine(pk, O.IOU_05_095, tuning=tv)
+        assert np.array_equal(ref, eng2.orie(N, ens_matrix=em)), tv
+        eng2.close()
+    eng.close()
+
+
 def test_class_sharded_sums_add_up():
     """Multi-GPU decomposition by class, emulated on one GPU: every shard keeps all images and its share of the
     classes; per-target AP sums of the shards add up to the un-sharded sums, so one all-reduce recovers the rewards."""
