@@ -334,7 +334,11 @@ def roofline_block(workload, world, dom, means, clk_mhz, info, pk, N, nt, hbm_pe
     sms = 148
     ctr = kernel_counters(workload).get(kname) if world == 1 else None
     nb = (nt + 31) // 32
-    slot_stream = float(nb) * float(info.get("slots", 0)) * 6.0           # image u32 + TP mask u16 per slot, per batch
+    # the slot stream is read once per batch — per PAIR of batches where two membership tables fit shared memory (or live
+    # in global memory) — as one packed 32-bit word per slot up to 65535 images, else image u32 + TP mask u16
+    table = ((pk.num_images + 1 + 31) // 32) * 32 * 4
+    pairs = table > 112 * 1024 or 2 * table <= 56 * 1024
+    slot_stream = float((nb + 1) // 2 if pairs else nb) * float(info.get("slots", 0)) * (4.0 if pk.num_images <= 65535 else 6.0)
     ev_touch = float(nt) * float(info.get("events", 0)) * 4.0 * (min(N, pk.num_images - 1) + 1) / max(pk.num_images, 1)
     seg_tab = float(info.get("segments", 0)) * float(nb * 32) * 8.0
     engine_bytes = {"walk_ms": slot_stream + ev_touch + seg_tab, "ap_ms": ev_touch + seg_tab,

@@ -36,7 +36,7 @@ class IndexInfo(C.Structure):
 
 class Tuning(C.Structure):
     _fields_ = [("seg_chunks", C.c_int32), ("sort_max_blocks", C.c_int32), ("post_blocks", C.c_int32),
-                ("walk_gmem", C.c_int32), ("ap_mode", C.c_int32), ("sort_lsd", C.c_int32), ("walk_unpacked", C.c_int32),
+                ("walk_gmem", C.c_int32), ("ap_mode", C.c_int32), ("sort_lsd", C.c_int32), ("walk_unpacked", C.c_int32), ("walk_single", C.c_int32),
                 ("walk_waves", C.c_double)]
 
 

@@ -839,6 +839,7 @@ static int index_create(int64_t M, int64_t C, int T, int64_t num_weak, int64_t n
     ix->cls_per_warp = 32 / T;
     ix->class_groups = ceil_div(C, ix->cls_per_warp);
     ix->walk_gmem = tune.walk_gmem;
+    ix->walk_single = tune.walk_single;
     ix->ap_mode = tune.ap_mode;
     ix->walk_waves = tune.walk_waves;
     const int rc = build(ix, w_off, w_cls, w_conf, w_tp, s_off, s_cls, s_conf, s_tp, l_off, l_cls, tune, tp_ready, stream, mem, plan);

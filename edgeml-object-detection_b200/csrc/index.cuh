@@ -78,7 +78,7 @@ struct orie_index {
     int64_t class_groups = 0;          // ceil(C / cls_per_warp)
 
     // ---- per-index tuning (orie_tuning_t; zeros = defaults)
-    int walk_gmem = 0, ap_mode = 0;
+    int walk_gmem = 0, ap_mode = 0, walk_single = 0;
     double walk_waves = 0.0;
 
     int64_t device_bytes = 0;

@@ -174,6 +174,7 @@ struct WalkParams {
     int64_t ens_words;
     const uint32_t *ens_bits;   // [nt][ens_words]
     uint32_t *memb_global;      // [ntp / 32][ens_words * 32] membership tables in global memory (GMEM kernels)
+    int memb_pairs;             // != 0: memb_global holds the tables of two batches side by side ([ntp / 64][ens_words * 32][2])
     // stream
     const uint32_t *slot_img;
     const int32_t *seg_chunk0, *seg_nch;
@@ -246,10 +247,16 @@ walk_kernel(const WalkParams p) {
         return;
     }
     if (yb * p.segs_per_block >= S) return;
+    // the targets' event lists are packed with the index's exact event count as their stride, whatever the capacity of
+    // the workspace (sized from an upper bound when the host has not waited for the build): the records of one call stay
+    // within a few hundred pages instead of one page per target
+    const int64_t ev_stride = DETS ? (int64_t)p.meta->Ev : 0;
     const int64_t tl = lb * 32 + lane;             // local target of this lane
     Transposer transpose;
     transpose.init(lane);
-    const uint32_t *memb = GMEM ? p.memb_global + lb * p.ens_words * 32 : memb_s;
+    const uint32_t *memb = !GMEM ? memb_s
+                           : p.memb_pairs ? p.memb_global + (lb >> 1) * p.ens_words * 64 + (lb & 1) : p.memb_global + lb * p.ens_words * 32;
+    const uint32_t memb_stride = GMEM && p.memb_pairs ? 2u : 1u;
     if (!GMEM) {
         const uint32_t *row = p.ens_bits + tl * p.ens_words;
         const bool live = tl < p.nt;
@@ -265,7 +272,7 @@ walk_kernel(const WalkParams p) {
     if (!GMEM)        // through an opaque move: otherwise the window base is re-derived in every trip of the slot loop
         asm volatile("mov.u32 %0, %1;" : "=r"(memb_sa) : "r"((uint32_t)__cvta_generic_to_shared(memb_s)));
     auto lookup = [&](uint32_t img) -> uint32_t {
-        if (GMEM) return __ldg(memb + img);
+        if (GMEM) return __ldg(memb + img * memb_stride);
         uint32_t v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(memb_sa + img * 4u));
         return v;
@@ -284,7 +291,7 @@ walk_kernel(const WalkParams p) {
         uint32_t *evout = nullptr;
         uint32_t ecur = 0;
         if (DETS) {
-            evout = p.ev + tl * p.Ev + p.seg_ev0[s];
+            evout = p.ev + tl * ev_stride + p.seg_ev0[s];
             asm volatile("" : "+l"(evout));        // kept in registers: otherwise re-derived for every record written
             const uint32_t *o = p.bqoff + gb * (p.S_cap + 1) + s;
             qi = o[0]; q_end = o[1];
@@ -367,6 +374,220 @@ walk_kernel(const WalkParams p) {
 #pragma unroll
             for (int t = 0; t < ORIE_MAX_THRESHOLDS; ++t)
                 if (t < p.T) ko[(int64_t)t * p.ntp] = (uint16_t)(kc[t >> 1] >> ((t & 1) * 16));
+        }
+    }
+}
+
+// ---- the detection walk for TWO batches (64 targets) per warp.  What does not depend on the target — the slot loads,
+// the loop and the search for the chunk's events — is paid once for both; the membership table holds the two batches'
+// words side by side (one 64-bit lookup), and the two bit transposes are independent instruction streams.  Used when two
+// tables fit shared memory four blocks to the SM (or live in global memory); same outputs as walk_kernel<true, ...>.
+__global__ void membership_table2_kernel(const WalkParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t lp = blockIdx.x, tlA = lp * 64 + lane, tlB = tlA + 32;
+    Transposer transpose;
+    transpose.init(lane);
+    const uint32_t *rowA = p.ens_bits + tlA * p.ens_words, *rowB = p.ens_bits + tlB * p.ens_words;
+    const bool liveA = tlA < p.nt, liveB = tlB < p.nt;
+    uint2 *out = (uint2 *)p.memb_global + lp * p.ens_words * 32;
+    for (int64_t w = (int64_t)blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); w < p.ens_words;
+         w += (int64_t)gridDim.y * (blockDim.x >> 5))
+        out[w * 32 + lane] = make_uint2(transpose(liveA ? rowA[w] : 0u), transpose(liveB ? rowB[w] : 0u));
+}
+
+// Own detections of one batch's 32 images inside one segment (walk2_kernel): a window of 32 entries of the batch's
+// query list, one per lane.  `wqc` = chunk of the lane's entry relative to the segment (INT_MAX beyond the end of the
+// list range), `next` (uniform) = chunk of the first entry that has not been handled.  An entry of image i is answered
+// by shuffling the running count and the membership word of lane i to the lane that holds the entry; all entries of a
+// chunk are answered in one step, and the list is read 32 entries at a time instead of one dependent load per entry.
+struct QueryWindow {
+    uint2 wq;
+    int wqc, next;
+    uint32_t base, end;
+    __device__ __forceinline__ void load(const uint2 *bq, uint32_t ch0, int lane) {
+        const uint32_t i = base + (uint32_t)lane;
+        wq = make_uint2(0u, 0u);
+        wqc = 0x7fffffff;
+        if (i < end) {
+            wq = bq[i];
+            wqc = (int)(((wq.x & 0x7fffffffu) >> 5) - ch0);
+        }
+    }
+    __device__ __forceinline__ void open(const uint2 *bq, uint32_t first, uint32_t last, uint32_t ch0, int lane) {
+        base = first; end = last;
+        load(bq, ch0, lane);
+        next = __reduce_min_sync(kFull, wqc);
+    }
+    __device__ __forceinline__ void chunk(const uint2 *bq, int c, uint32_t ch0, int lane, uint32_t word, uint32_t cnt,
+                                          uint32_t *cb_w, uint32_t *cb_s) {
+        while (next == c) {                   // uniform
+            const bool hit = wqc == c;
+            const int src = (int)(wq.y >> 27);
+            const uint32_t wsrc = __shfl_sync(kFull, word, src), csrc = __shfl_sync(kFull, cnt, src);
+            if (hit) ((wq.x >> 31) ? cb_s : cb_w)[wq.y & 0x07ffffffu] = csrc + __popc(wsrc & ((1u << (wq.x & 31u)) - 1u));
+            int from = c + 1;                 // entries of chunk c in this window are done ...
+            if (__shfl_sync(kFull, wqc, 31) <= c) {      // ... and so is the window: the next 32 entries (may continue chunk c)
+                base += 32u;
+                load(bq, ch0, lane);
+                from = c;
+            }
+            next = __reduce_min_sync(kFull, wqc >= from ? wqc : 0x7fffffff);
+        }
+    }
+};
+
+#ifndef ORIE_WALK2_PIPE
+#define ORIE_WALK2_PIPE 1
+#endif
+constexpr int kWalk2Threads = 256, kWalk2Blocks = 4;
+template <bool GMEM, bool PACKED>
+__global__ void __launch_bounds__(kWalk2Threads, kWalk2Blocks)
+walk2_kernel(const WalkParams p) {
+    extern __shared__ uint2 memb2_s[];     // [ens_words * 32]: .x / .y = membership words of the pair's two batches
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kWalk2Threads / 32;
+    const int64_t lp = GMEM ? blockIdx.y : blockIdx.x;   // local batch pair
+    const int64_t yb = GMEM ? blockIdx.x : blockIdx.y;   // segment group
+    const uint32_t status = p.meta->status;
+    const int64_t S = p.meta->S;
+    if (status & (kStatusRows | kStatusClass | kStatusCounts)) return;
+    if ((int64_t)p.meta->Ev > p.Ev) {
+        if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicOr(&p.meta->status, kStatusWorkspace);
+        return;
+    }
+    if (yb * p.segs_per_block >= S) return;
+    const int64_t ev_stride = (int64_t)p.meta->Ev;        // packed event lists (see walk_kernel)
+    const int64_t tlA = lp * 64 + lane, tlB = tlA + 32;   // local targets of this lane
+    const bool hasB = lp * 64 + 32 < p.ntp;              // the pair's second batch exists in this call
+    Transposer transpose;
+    transpose.init(lane);
+    const uint2 *memb = GMEM ? (const uint2 *)p.memb_global + lp * p.ens_words * 32 : memb2_s;
+    if (!GMEM) {
+        const uint32_t *rowA = p.ens_bits + tlA * p.ens_words, *rowB = p.ens_bits + tlB * p.ens_words;
+        const bool liveA = tlA < p.nt, liveB = tlB < p.nt;
+        for (int64_t w = warp; w < p.ens_words; w += kWarps)
+            memb2_s[w * 32 + lane] = make_uint2(transpose(liveA ? rowA[w] : 0u), transpose(liveB ? rowB[w] : 0u));
+        __syncthreads();
+    }
+    uint32_t memb_sa = 0u;
+    if (!GMEM) asm volatile("mov.u32 %0, %1;" : "=r"(memb_sa) : "r"((uint32_t)__cvta_generic_to_shared(memb2_s)));
+    auto lookup = [&](uint32_t img) -> uint2 {
+        if (GMEM) return __ldg(memb + img);
+        uint2 v;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(memb_sa + img * 8u));
+        return v;
+    };
+    const uint32_t sentinel = (uint32_t)p.M;
+    const int64_t gbA = (p.t0 >> 5) + lp * 2;      // global batch of the first of the two
+    const int64_t sbeg = yb * p.segs_per_block;
+    const int64_t send = min(sbeg + p.segs_per_block, S);
+    for (int64_t s = sbeg + warp; s < send; s += kWarps) {
+        const int64_t ch0 = p.seg_chunk0[s];
+        const int nch = p.seg_nch[s];
+        uint32_t cntA = 0, cntB = 0, ecurA = 0, ecurB = 0;
+        // own detections (weak: sitting in a slot, strong: inserted in front of one) of each batch's 32 images whose slot
+        // lies in this segment, ascending by slot: a window of 32 list entries per batch, one per lane, with the chunk
+        // (relative to the segment) of the lane's entry and, uniform, the chunk of the first entry not yet handled
+        QueryWindow qA, qB;
+        const uint32_t ev0 = p.seg_ev0[s];
+        uint32_t *evoutA = p.ev + tlA * ev_stride + ev0, *evoutB = p.ev + tlB * ev_stride + ev0;
+        asm volatile("" : "+l"(evoutA), "+l"(evoutB));
+        {
+            const uint32_t *o = p.bqoff + gbA * (p.S_cap + 1) + s;
+            qA.open(p.bq, o[0], o[1], (uint32_t)ch0, lane);
+            if (hasB) qB.open(p.bq, o[p.S_cap + 1], o[p.S_cap + 2], (uint32_t)ch0, lane);
+            else qB.open(p.bq, 0u, 0u, (uint32_t)ch0, lane);
+        }
+        const uint32_t *sp = (PACKED ? p.slot_pk : p.slot_img) + ch0 * 32 + lane;
+        const uint16_t *stp = PACKED ? nullptr : p.slot_tp + ch0 * 32 + lane;
+#if ORIE_WALK2_PIPE
+        // software pipeline, two deep: the slot words of chunk c + 2 are in flight, the table lookup and the two bit
+        // transposes of chunk c + 1 are issued before the events and own detections of chunk c are worked on (their
+        // shuffle latency hides behind that work); past the end of the segment the pipeline is fed sentinels
+        uint32_t xc = sp[0], xn = nch > 1 ? sp[32] : sentinel;
+        uint32_t tc = 0u, tn = 0u;
+        if (!PACKED) { tc = stp[0]; tn = nch > 1 ? (uint32_t)stp[32] : 0u; }
+        uint32_t wordA, wordB;                     // bit l: slot l holds a member of MY target
+        {
+            const uint2 w2 = lookup(PACKED ? xc & 0xffffu : xc);
+            wordA = transpose(w2.x); wordB = transpose(w2.y);
+        }
+        for (int c = 0; c < nch; ++c) {
+            const uint32_t tpv = PACKED ? xc : tc << 16;   // TP mask of MY slot in bits 16..31
+            xc = xn; tc = tn;
+            sp += 32;
+            xn = c + 2 < nch ? sp[32] : sentinel;
+            if (!PACKED) {
+                stp += 32;
+                tn = c + 2 < nch ? (uint32_t)stp[32] : 0u;
+            }
+            const uint2 n2 = lookup(PACKED ? xc & 0xffffu : xc);
+            const uint32_t nextA = transpose(n2.x), nextB = transpose(n2.y);
+#else
+        uint32_t xn = sp[0], tn = PACKED ? 0u : (uint32_t)stp[0];
+        for (int c = 0; c < nch; ++c) {
+            const uint32_t x = xn;
+            const uint32_t tpv = PACKED ? x : tn << 16;    // TP mask of MY slot in bits 16..31
+            sp += 32;
+            if (c + 1 < nch) xn = sp[0];
+            if (!PACKED) {
+                stp += 32;
+                if (c + 1 < nch) tn = stp[0];
+            }
+            const uint2 w2 = lookup(PACKED ? x & 0xffffu : x);
+            const uint32_t wordA = transpose(w2.x), wordB = transpose(w2.y);   // bit l: slot l holds a member of MY target
+#endif
+            uint32_t eb = __ballot_sync(kFull, tpv >= 0x10000u);               // slots of the chunk holding an event
+            while (eb) {
+                const int b = __ffs(eb) - 1;
+                eb &= eb - 1;
+                const uint32_t m = __shfl_sync(kFull, tpv, b) & 0xffff0000u;
+                const uint32_t sa = wordA << (31 - b), sb = wordB << (31 - b);  // slot b on top, the slots behind it shifted out
+                if ((int)sa < 0) evoutA[ecurA++] = (cntA + __popc(sa)) | m;     // 1-based rank <= 65504 (index.cu)
+                if ((int)sb < 0) evoutB[ecurB++] = (cntB + __popc(sb)) | m;
+            }
+            qA.chunk(p.bq, c, (uint32_t)ch0, lane, wordA, cntA, p.cb_w, p.cb_s);
+            qB.chunk(p.bq, c, (uint32_t)ch0, lane, wordB, cntB, p.cb_w, p.cb_s);
+            cntA += __popc(wordA);
+            cntB += __popc(wordB);
+#if ORIE_WALK2_PIPE
+            wordA = nextA; wordB = nextB;
+#endif
+        }
+        p.tot[s * p.ntp + tlA] = cntA;
+        p.evcnt[s * p.ntp + tlA] = ecurA;
+        if (hasB) {
+            p.tot[s * p.ntp + tlB] = cntB;
+            p.evcnt[s * p.ntp + tlB] = ecurB;
+        }
+        // member true positives per threshold (see walk_kernel)
+        const uint32_t e0 = ev0, e1 = p.seg_ev0[s + 1];
+        uint32_t kcA[ORIE_MAX_THRESHOLDS / 2], kcB[ORIE_MAX_THRESHOLDS / 2];
+#pragma unroll
+        for (int i = 0; i < ORIE_MAX_THRESHOLDS / 2; ++i) kcA[i] = kcB[i] = 0u;
+        for (uint32_t w0 = e0 & ~31u; w0 < e1; w0 += 32u) {
+            const uint32_t e = w0 + lane;
+            const bool in = e >= e0 && e < e1;
+            const uint32_t img = in ? p.ev_img[e] : sentinel;
+            const uint32_t mask = in ? (uint32_t)p.ev_mask[e] : 0u;
+            const uint2 w2 = lookup(img);
+            const uint32_t wordA = transpose(w2.x), wordB = transpose(w2.y);
+#pragma unroll
+            for (int t = 0; t < ORIE_MAX_THRESHOLDS; ++t) {
+                if (t < p.T) {          // uniform
+                    const uint32_t tb = __ballot_sync(kFull, (mask >> t) & 1u);
+                    kcA[t >> 1] += (uint32_t)__popc(wordA & tb) << ((t & 1) * 16);
+                    kcB[t >> 1] += (uint32_t)__popc(wordB & tb) << ((t & 1) * 16);
+                }
+            }
+        }
+        uint16_t *ko = p.kseg + (s * p.T) * p.ntp + tlA;
+#pragma unroll
+        for (int t = 0; t < ORIE_MAX_THRESHOLDS; ++t) {
+            if (t < p.T) {
+                ko[(int64_t)t * p.ntp] = (uint16_t)(kcA[t >> 1] >> ((t & 1) * 16));
+                if (hasB) ko[(int64_t)t * p.ntp + 32] = (uint16_t)(kcB[t >> 1] >> ((t & 1) * 16));
+            }
         }
     }
 }
@@ -508,10 +729,13 @@ struct OwnCursor {
     }
 };
 
-constexpr int kApThreads = 128;
-#ifndef ORIE_AP_BLOCKS
-#define ORIE_AP_BLOCKS 8
+#ifndef ORIE_AP_THREADS
+#define ORIE_AP_THREADS 128
 #endif
+#ifndef ORIE_AP_BLOCKS
+#define ORIE_AP_BLOCKS (1024 / ORIE_AP_THREADS)
+#endif
+constexpr int kApThreads = ORIE_AP_THREADS;
 
 // One warp per (target, group of 32/T classes); lane = (class slot, IoU threshold).
 //
@@ -548,7 +772,8 @@ ap_kernel(const ApParams p, const Grid101 grid) {
     const int64_t tl = item / p.class_groups, grp = item % p.class_groups;
     const int64_t j = p.t0 + tl;
     const uint32_t *tot = p.tot + tl, *evcnt = p.evcnt + tl;
-    const uint32_t *ev = p.ev + tl * p.Ev;
+    // the lists are laid out with the exact event count of the index as their stride (walk_kernel)
+    const uint32_t *ev = p.ev + tl * (int64_t)p.meta->Ev;
 
     // ---- classes with ground truth in E + {target}: lane = class
     double has_gt = 0.0;
@@ -766,7 +991,7 @@ static WsLayout ws_layout(const orie_index *ix, int64_t nt) {
     L.cb_s = take(ix->Ds * 4);
     L.partial = take(ntp * ix->class_groups * 3 * 8);
     // membership tables in global memory, only when they exceed shared memory (or when forced for tests)
-    L.memb = take(walk_in_gmem(ix) ? (ntp / 32) * ix->ens_words * 32 * 4 : 0);
+    L.memb = take(walk_in_gmem(ix) ? round_up(ntp / 32, 2) * ix->ens_words * 32 * 4 : 0);     // whole batch pairs
     L.ev = o;
     L.fixed = o;
     return L;
@@ -794,6 +1019,8 @@ static int walk_attributes() {
     ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 512, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ORIE_CUDA(cudaFuncSetAttribute(walk_kernel<false, 1024, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ORIE_CUDA(cudaFuncSetAttribute(walk2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     done[dev] = true;
     return ORIE_OK;
 }
@@ -956,15 +1183,17 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     wp.ens_words = ix->ens_words; wp.ens_bits = ens_bits;
     const int64_t nb = ntp / 32;
     const int walk_threads = gmem ? 256 : smem <= 56 * 1024 ? 256 : 512;   // keep the SM full of warps
-    auto segs_per_block = [&](int64_t S) {
-        // enough blocks for two full waves of resident blocks (2048 threads per SM) when the data allows,
-        // at least one segment per warp
-        const int64_t resident = 148 * (kWalkResident / walk_threads > 0 ? kWalkResident / walk_threads : 1);
+    // the detection walk takes two batches per warp when two tables fit shared memory four blocks to the SM
+    const bool pairs = !ix->walk_single && (gmem || 2 * smem <= 56 * 1024);
+    auto segs_per_block = [&](int64_t S, bool two) {
+        // enough blocks for two full waves of resident blocks when the data allows, at least one segment per warp
+        const int64_t resident = two ? 148 * kWalk2Blocks : 148 * (kWalkResident / walk_threads > 0 ? kWalkResident / walk_threads : 1);
+        const int64_t nb = two ? ceil_div(ntp / 32, 2) : ntp / 32;
         const double waves = ix->walk_waves > 0.0 ? ix->walk_waves : 2.0;
         int64_t want_y = (int64_t)((waves * (double)resident + (double)nb - 1.0) / (double)nb);
         if (gmem) want_y = std::max<int64_t>(want_y, 32);     // many blocks per batch: few tables in flight
         int64_t spb = ceil_div(S, want_y > 0 ? want_y : 1);
-        const int64_t warps = walk_threads / 32;
+        const int64_t warps = two ? kWalk2Threads / 32 : walk_threads / 32;
         spb = round_up(spb > 0 ? spb : 1, warps);
         return (int)spb;
     };
@@ -976,10 +1205,13 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     // launch grids come from the exact segment counts when the host already knows them, else from their upper bounds
     const int64_t S_grid = ix->resolved ? ix->S : ix->S_cap, SL_grid = ix->resolved ? ix->SL : ix->SL_cap;
     if (marks) ORIE_CUDA(cudaEventRecord(marks[0], stream));
+    const int64_t nb2 = ceil_div(nb, 2);
     if (gmem) {
         wp.memb_global = (uint32_t *)(ws + L.memb);
-        dim3 grid((unsigned)nb, (unsigned)std::min<int64_t>(ceil_div(ix->ens_words, 8), 64));
-        membership_table_kernel<<<grid, 256, 0, stream>>>(wp);
+        wp.memb_pairs = pairs ? 1 : 0;
+        dim3 grid((unsigned)(pairs ? nb2 : nb), (unsigned)std::min<int64_t>(ceil_div(ix->ens_words, 8), 64));
+        if (pairs) membership_table2_kernel<<<grid, 256, 0, stream>>>(wp);
+        else membership_table_kernel<<<grid, 256, 0, stream>>>(wp);
         ORIE_LAUNCH_CHECK();
     }
     // labels: a small grid — on the auxiliary stream, if the caller gave one, it runs next to the detection walk
@@ -990,7 +1222,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     if (SL_grid > 0) {
         WalkParams lp = wp;
         lp.slot_img = ix->lab_slot_img; lp.seg_chunk0 = ix->lseg_chunk0; lp.seg_nch = ix->lseg_nch;
-        lp.segs_per_block = segs_per_block(SL_grid);
+        lp.segs_per_block = segs_per_block(SL_grid, false);
         lp.tot = (uint32_t *)(ws + L.totL);
         const unsigned ny = (unsigned)ceil_div(SL_grid, lp.segs_per_block);
         dim3 grid = gmem ? dim3(ny, (unsigned)nb) : dim3((unsigned)nb, ny);
@@ -1008,7 +1240,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     // detections
     {
         wp.slot_img = ix->slot_img; wp.seg_chunk0 = ix->seg_chunk0; wp.seg_nch = ix->seg_nch;
-        wp.segs_per_block = segs_per_block(S_grid);
+        wp.segs_per_block = segs_per_block(S_grid, pairs);
         wp.tot = (uint32_t *)(ws + L.tot);
         wp.slot_tp = ix->slot_tp; wp.slot_pk = ix->slot_pk; wp.seg_ev0 = ix->seg_ev0;
         wp.ev_img = ix->ev_img; wp.ev_mask = ix->ev_mask; wp.T = ix->T;
@@ -1020,8 +1252,16 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         wp.cb_w = (uint32_t *)(ws + L.cb_w);
         wp.cb_s = (uint32_t *)(ws + L.cb_s);
         const unsigned ny = (unsigned)ceil_div(S_grid, wp.segs_per_block);
-        dim3 grid = gmem ? dim3(ny, (unsigned)nb) : dim3((unsigned)nb, ny);
-        ORIE_TRY(launch_walk<true>(grid, walk_threads, smem, gmem, stream, wp));
+        if (pairs) {
+            dim3 grid = gmem ? dim3(ny, (unsigned)nb2) : dim3((unsigned)nb2, ny);
+            if (gmem && wp.slot_pk) walk2_kernel<true, true><<<grid, kWalk2Threads, 0, stream>>>(wp);
+            else if (gmem) walk2_kernel<true, false><<<grid, kWalk2Threads, 0, stream>>>(wp);
+            else if (wp.slot_pk) walk2_kernel<false, true><<<grid, kWalk2Threads, 2 * smem, stream>>>(wp);
+            else walk2_kernel<false, false><<<grid, kWalk2Threads, 2 * smem, stream>>>(wp);
+        } else {
+            dim3 grid = gmem ? dim3(ny, (unsigned)nb) : dim3((unsigned)nb, ny);
+            ORIE_TRY(launch_walk<true>(grid, walk_threads, smem, gmem, stream, wp));
+        }
         ORIE_LAUNCH_CHECK();
     }
     if (side && SL_grid > 0) ORIE_CUDA(cudaStreamWaitEvent(stream, ix->ev_join, 0));

@@ -1,5 +1,5 @@
 """Developer tool (not part of the product path): A/B timings of kernel variants inside one process.
-    python profiles/ab.py [workload]
+    python profiles/ab.py [workload] ['[{"walk_single": 1}, {"walk_waves": 3.0}]' | seg_chunks list "0,64"]
 Prints per-kernel medians (orie_reward_profile) for tuning variants and the match+index phase time."""
 import os, sys, json
 import numpy as np
@@ -16,7 +16,8 @@ dev = torch.device("cuda:0")
 dp = DevicePacked(HostPacked(pk), dev)
 torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-variants = [dict(seg_chunks=c) for c in [int(x) for x in (sys.argv[2].split(',') if len(sys.argv) > 2 else ['0'])]]
+arg = sys.argv[2] if len(sys.argv) > 2 else "0"
+variants = json.loads(arg) if arg.lstrip().startswith("[") else [dict(seg_chunks=int(x)) for x in arg.split(",")]
 ref = None
 for tv in variants:
     rows, idx = [], []

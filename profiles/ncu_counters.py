@@ -18,7 +18,7 @@ import sys
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "r02_kernel_counters.json")
 KERNELS = ["walk_kernel", "ap_kernel", "match_kernel", "coop_radix_kernel", "post_kernel", "prep_kernel", "ens_sample_kernel",
-           "finalize_kernel", "class_sort_kernel", "layout_kernel", "partition_kernel"]
+           "finalize_kernel", "layout_kernel", "bucket_partition_kernel", "bucket_local_kernel", "bucket_local_cta_kernel"]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "usecond": 1.0, "us": 1.0, "nsecond": 1e-3, "ns": 1e-3,
          "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6}
 
@@ -45,8 +45,9 @@ def summarise(launches):
     out = {}
     for k in KERNELS:
         mine = [(m, name) for (_, name), m in launches.items() if k in name and "membership" not in name]
-        if k == "walk_kernel":      # the detection walk (DETS = true), not the label walk
-            mine = [(m, name) for m, name in mine if "walk_kernel<1" in name or "walk_kernel<(bool)1" in name]
+        if k == "walk_kernel":      # the detection walk (two batches per warp, or DETS = true), not the label walk
+            mine = [(m, name) for (_, name), m in launches.items()
+                    if "walk2_kernel" in name or "walk_kernel<1" in name or "walk_kernel<(bool)1" in name]
         if not mine:
             continue
         m, name = max(mine, key=lambda t: t[0].get("smsp__inst_executed.sum", 0.0))

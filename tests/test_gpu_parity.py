@@ -124,18 +124,25 @@ def test_global_memory_membership_table_matches():
     eng.close(); eng2.close()
 
 
-def test_unpacked_slot_stream_matches():
-    """Up to 65535 images the walk reads one 32-bit word per slot (image | TP mask << 16); larger datasets read the two
-    arrays.  Force the two-array path (shared- and global-memory table) on a small dataset: identical bits."""
+def test_walk_variants_match():
+    """The detection walk has four code paths: one or two 32-target batches per warp (two when two membership tables
+    fit shared memory), slot image + TP mask in one packed word (up to 65535 images) or in two arrays, and for each the
+    membership table in shared or in global memory.  Force every combination on a small dataset (an odd number of
+    batches, so the last pair is half empty): identical bits, and right against the oracle."""
     M, N = 140, 60
     _, pk = make_packed(M=M, seed=45)
     eng = _engine(pk, O.IOU_05_095)
     em = O.ensemble_matrix(M, N, 10)
     ref = eng.orie(N, ens_matrix=em)
-    for tv in (dict(walk_unpacked=1), dict(walk_unpacked=1, walk_gmem=1)):
-        eng2 = _engine(pk, O.IOU_05_095, tuning=tv)
-        assert np.array_equal(ref, eng2.orie(N, ens_matrix=em)), tv
-        eng2.close()
+    wd, sd, lc = oracle_cache(pk, O.IOU_05_095)
+    assert np.abs(ref - O.orie_all(wd, sd, lc, em)).max() < 1e-9
+    for single in (0, 1):
+        for unpacked in (0, 1):
+            for gmem in (0, 1):
+                tv = dict(walk_single=single, walk_unpacked=unpacked, walk_gmem=gmem)
+                eng2 = _engine(pk, O.IOU_05_095, tuning=tv)
+                assert np.array_equal(ref, eng2.orie(N, ens_matrix=em)), tv
+                eng2.close()
     eng.close()
 
 
