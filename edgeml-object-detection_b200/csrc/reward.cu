@@ -444,6 +444,7 @@ template <bool GMEM, bool PACKED>
 __global__ void __launch_bounds__(kWalk2Threads, kWalk2Blocks)
 walk2_kernel(const WalkParams p) {
     extern __shared__ uint2 memb2_s[];     // [ens_words * 32]: .x / .y = membership words of the pair's two batches
+    __shared__ int next_seg;               // the block's segments are handed to its warps as they become free
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarps = kWalk2Threads / 32;
     const int64_t lp = GMEM ? blockIdx.y : blockIdx.x;   // local batch pair
@@ -456,6 +457,7 @@ walk2_kernel(const WalkParams p) {
         return;
     }
     if (yb * p.segs_per_block >= S) return;
+    if (threadIdx.x == 0) next_seg = 0;
     const int64_t ev_stride = (int64_t)p.meta->Ev;        // packed event lists (see walk_kernel)
     const int64_t tlA = lp * 64 + lane, tlB = tlA + 32;   // local targets of this lane
     const bool hasB = lp * 64 + 32 < p.ntp;              // the pair's second batch exists in this call
@@ -467,8 +469,8 @@ walk2_kernel(const WalkParams p) {
         const bool liveA = tlA < p.nt, liveB = tlB < p.nt;
         for (int64_t w = warp; w < p.ens_words; w += kWarps)
             memb2_s[w * 32 + lane] = make_uint2(transpose(liveA ? rowA[w] : 0u), transpose(liveB ? rowB[w] : 0u));
-        __syncthreads();
     }
+    __syncthreads();
     uint32_t memb_sa = 0u;
     if (!GMEM) asm volatile("mov.u32 %0, %1;" : "=r"(memb_sa) : "r"((uint32_t)__cvta_generic_to_shared(memb2_s)));
     auto lookup = [&](uint32_t img) -> uint2 {
@@ -481,7 +483,13 @@ walk2_kernel(const WalkParams p) {
     const int64_t gbA = (p.t0 >> 5) + lp * 2;      // global batch of the first of the two
     const int64_t sbeg = yb * p.segs_per_block;
     const int64_t send = min(sbeg + p.segs_per_block, S);
-    for (int64_t s = sbeg + warp; s < send; s += kWarps) {
+    // segments of one class have equal length but classes differ: a fixed split over the warps leaves warps idle until the
+    // block's longest share is done, so every warp takes the block's next segment when it becomes free
+    for (;;) {
+        int take = 0;
+        if (lane == 0) take = atomicAdd(&next_seg, 1);
+        const int64_t s = sbeg + __shfl_sync(kFull, take, 0);
+        if (s >= send) break;
         const int64_t ch0 = p.seg_chunk0[s];
         const int nch = p.seg_nch[s];
         uint32_t cntA = 0, cntB = 0, ecurA = 0, ecurB = 0;
@@ -1193,8 +1201,8 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         int64_t want_y = (int64_t)((waves * (double)resident + (double)nb - 1.0) / (double)nb);
         if (gmem) want_y = std::max<int64_t>(want_y, 32);     // many blocks per batch: few tables in flight
         int64_t spb = ceil_div(S, want_y > 0 ? want_y : 1);
-        const int64_t warps = two ? kWalk2Threads / 32 : walk_threads / 32;
-        spb = round_up(spb > 0 ? spb : 1, warps);
+        // the single-batch kernel splits a block's segments evenly over its warps; the pair kernel hands them out one by one
+        spb = two ? std::max<int64_t>(spb, kWalk2Threads / 32) : round_up(spb > 0 ? spb : 1, walk_threads / 32);
         return (int)spb;
     };
     if (gmem && nb > 65535) {
