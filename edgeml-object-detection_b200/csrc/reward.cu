@@ -942,24 +942,34 @@ __device__ __forceinline__ double reward_from_sums(double sw, double ss, double 
     return __dmul_rn(__dsub_rn(__ddiv_rn(ss, cnt), __ddiv_rn(sw, cnt)), (double)(N + 1));
 }
 
-__global__ void finalize_kernel(const double *__restrict__ partial, int64_t nt, int64_t groups, int T, int64_t N,
-                                const IndexMeta *__restrict__ meta, double *__restrict__ reward, double *__restrict__ detail) {
-    const int64_t tl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per target: lane g adds the partial sums of class groups g, g + 32, ...; a fixed shuffle tree adds the lanes
+// (the order of the additions depends on the number of groups only, never on how targets are cut into calls).
+constexpr int kFinalizeThreads = 128;
+__global__ void __launch_bounds__(kFinalizeThreads)
+finalize_kernel(const double *__restrict__ partial, int64_t nt, int64_t groups, int T, int64_t N,
+                const IndexMeta *__restrict__ meta, double *__restrict__ reward, double *__restrict__ detail) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tl = (int64_t)blockIdx.x * (kFinalizeThreads / 32) + (threadIdx.x >> 5);
     if (tl >= nt) return;
     double sw = 0.0, ss = 0.0, nc = 0.0;
     if (meta->status) {                         // nothing was computed: make that impossible to miss
         sw = ss = nc = __longlong_as_double(0x7ff8000000000000ll);
-        if (reward) reward[tl] = sw;
-        if (detail) { detail[tl * 3] = sw; detail[tl * 3 + 1] = ss; detail[tl * 3 + 2] = nc; }
-        return;
+    } else {
+        for (int64_t g = lane; g < groups; g += 32) {
+            const double *q = partial + (tl * groups + g) * 3;
+            sw = __dadd_rn(sw, q[0]);
+            ss = __dadd_rn(ss, q[1]);
+            nc += q[2];
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            sw = __dadd_rn(sw, __shfl_xor_sync(kFull, sw, d));
+            ss = __dadd_rn(ss, __shfl_xor_sync(kFull, ss, d));
+            nc += __shfl_xor_sync(kFull, nc, d);
+        }
     }
-    for (int64_t g = 0; g < groups; ++g) {
-        const double *q = partial + (tl * groups + g) * 3;
-        sw = __dadd_rn(sw, q[0]);
-        ss = __dadd_rn(ss, q[1]);
-        nc += q[2];
-    }
-    if (reward) reward[tl] = reward_from_sums(sw, ss, nc, T, N);
+    if (lane != 0) return;
+    if (reward) reward[tl] = meta->status ? sw : reward_from_sums(sw, ss, nc, T, N);
     if (detail) { detail[tl * 3] = sw; detail[tl * 3 + 1] = ss; detail[tl * 3 + 2] = nc; }
 }
 
@@ -1299,7 +1309,8 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     else ap_kernel<false, 2><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());      // default: depth-ordered active classes
     ORIE_LAUNCH_CHECK();
     if (marks) ORIE_CUDA(cudaEventRecord(marks[3], stream));
-    finalize_kernel<<<(unsigned)ceil_div(nt, 128), 128, 0, stream>>>(ap.partial, nt, ix->class_groups, ix->T, N, ix->meta, reward, detail);
+    finalize_kernel<<<(unsigned)ceil_div(nt, kFinalizeThreads / 32), kFinalizeThreads, 0, stream>>>(ap.partial, nt, ix->class_groups, ix->T, N, ix->meta,
+                                                                                                   reward, detail);
     ORIE_LAUNCH_CHECK();
     if (marks) ORIE_CUDA(cudaEventRecord(marks[4], stream));
     return ORIE_OK;

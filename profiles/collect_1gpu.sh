@@ -8,10 +8,10 @@
 T=${1:-r02}
 O=gpurun_out
 M=smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
-for wl in coco5000 voc4952 smoke500; do
+for wl in coco5000 voc4952 smoke500 coco5000_ori coco5000_dcsb; do
     ncu --metrics $M --clock-control none --csv --log-file $O/${T}_ctr_$wl.csv python bench.py --workload $wl --steps 1 --warmup 1 --no-cpu-baseline --no-graph > $O/${T}_ctr_$wl.log 2>&1
 done
-python profiles/ncu_counters.py coco5000 $O/${T}_ctr_coco5000.csv voc4952 $O/${T}_ctr_voc4952.csv smoke500 $O/${T}_ctr_smoke500.csv > $O/${T}_ctr_summary.txt 2>&1
+python profiles/ncu_counters.py coco5000 $O/${T}_ctr_coco5000.csv voc4952 $O/${T}_ctr_voc4952.csv smoke500 $O/${T}_ctr_smoke500.csv coco5000_ori $O/${T}_ctr_coco5000_ori.csv coco5000_dcsb $O/${T}_ctr_coco5000_dcsb.csv > $O/${T}_ctr_summary.txt 2>&1
 cp profiles/r02_kernel_counters.json $O/${T}_kernel_counters.json
 for wl in coco5000 smoke500 voc4952 coco5000_ori coco5000_dcsb; do
     python bench.py --workload $wl --steps 20 --warmup 5 > $O/${T}_bench_${wl}_1gpu.json 2> $O/${T}_bench_${wl}_1gpu.err
