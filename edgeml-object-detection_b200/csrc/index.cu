@@ -557,6 +557,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     }
     DeviceState *ds = nullptr;
     ORIE_TRY(device_state(&ds));
+    ix->sms = ds->sms;
     const int64_t n = Dw + Ds;
     const int64_t Nmax = std::max<int64_t>(std::max(n, G), 1);
     const Dets dets{Dw, Ds, w_cls, s_cls, w_conf, s_conf, w_tp, s_tp};

@@ -79,6 +79,7 @@ struct orie_index {
 
     // ---- per-index tuning (orie_tuning_t; zeros = defaults)
     int walk_gmem = 0, ap_mode = 0, walk_single = 0;
+    int sms = 0;                       // multiprocessors of the device (grid of the persistent AP kernel)
     double walk_waves = 0.0;
 
     int64_t device_bytes = 0;

@@ -194,6 +194,7 @@ struct WalkParams {
     uint32_t *ev;               // [ntp][Ev] event records: rank inside the segment (16 bits) | TP mask << 16
     uint16_t *kseg;             // [S][T][ntp] member true positives of the segment per IoU threshold
     uint32_t *cb_w, *cb_s;
+    unsigned long long *ap_counter;   // work counter of the AP kernel that follows: zeroed here
 };
 
 
@@ -247,6 +248,7 @@ walk_kernel(const WalkParams p) {
         return;
     }
     if (yb * p.segs_per_block >= S) return;
+    if (DETS && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.ap_counter = 0ull;
     // the targets' event lists are packed with the index's exact event count as their stride, whatever the capacity of
     // the workspace (sized from an upper bound when the host has not waited for the build): the records of one call stay
     // within a few hundred pages instead of one page per target
@@ -457,6 +459,7 @@ walk2_kernel(const WalkParams p) {
         return;
     }
     if (yb * p.segs_per_block >= S) return;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.ap_counter = 0ull;
     if (threadIdx.x == 0) next_seg = 0;
     const int64_t ev_stride = (int64_t)p.meta->Ev;        // packed event lists (see walk_kernel)
     const int64_t tlA = lp * 64 + lane, tlB = tlA + 32;   // local targets of this lane
@@ -627,6 +630,7 @@ struct ApParams {
     const uint16_t *own_w_cs, *own_s_cs, *own_w_m, *own_s_m;
     const uint32_t *own_w_q, *own_s_q, *cb_w, *cb_s;
     double *partial;    // [ntp][class_groups][3]
+    unsigned long long *next_item;   // work counter of the persistent warps (zero on entry)
     uint32_t *depths;   // measurement only (orie_reward_depths): [nt][C][T][2] loop trips of the sweep / its tail
 };
 
@@ -775,9 +779,21 @@ ap_kernel(const ApParams p, const Grid101 grid) {
     __syncthreads();
     const uint32_t *ge = grid.ge[4] ? nullptr : ge_s;      // uniform
     const int lane = threadIdx.x & 31;
-    const int64_t item = (int64_t)blockIdx.x * (kApThreads / 32) + (threadIdx.x >> 5);
-    if (item >= p.nt * p.class_groups) return;
-    const int64_t tl = item / p.class_groups, grp = item % p.class_groups;
+    // Persistent warps: every warp takes the next (class group, target) item from a counter in global memory (zeroed by
+    // the walk) until none is left.  A target's first group holds its deepest sweeps (act_cls), and the items are
+    // numbered group-major, so the long items are handed out first and the short ones fill the end; and a warp that
+    // finishes a short item does not wait for the longest item of its block to free the slot.
+    const int64_t items = p.nt * p.class_groups;
+    for (;;) {
+    unsigned long long took = 0;
+    if (lane == 0) took = atomicAdd(p.next_item, 1ull);
+    const int64_t item = (int64_t)__shfl_sync(kFull, took, 0);
+    if (item >= items) break;
+#ifdef ORIE_AP_TARGET_MAJOR
+    const int64_t tl = item / p.class_groups, grp = item - tl * p.class_groups;
+#else
+    const int64_t grp = item / p.nt, tl = item - grp * p.nt;
+#endif
     const int64_t j = p.t0 + tl;
     const uint32_t *tot = p.tot + tl, *evcnt = p.evcnt + tl;
     // the lists are laid out with the exact event count of the index as their stride (walk_kernel)
@@ -929,6 +945,7 @@ ap_kernel(const ApParams p, const Grid101 grid) {
         double *out = p.partial + (tl * p.class_groups + grp) * 3;
         out[0] = ap_w; out[1] = ap_s; out[2] = has_gt;
     }
+    }
 }
 
 // ----------------------------------------------------------------------------
@@ -987,7 +1004,7 @@ __global__ void rewards_from_sums_kernel(const double *__restrict__ sums, int64_
 // whatever the caller's workspace has left (at least the index's event count, checked on the host once the exact
 // count is known, on the device otherwise).
 struct WsLayout {
-    size_t tot, evcnt, totL, kseg, cb_w, cb_s, partial, memb, ev, fixed;
+    size_t tot, evcnt, totL, kseg, cb_w, cb_s, partial, counter, memb, ev, fixed;
 };
 
 static bool walk_in_gmem(const orie_index *ix) {
@@ -1008,6 +1025,7 @@ static WsLayout ws_layout(const orie_index *ix, int64_t nt) {
     L.cb_w = take(ix->Dw * 4);
     L.cb_s = take(ix->Ds * 4);
     L.partial = take(ntp * ix->class_groups * 3 * 8);
+    L.counter = take(8);
     // membership tables in global memory, only when they exceed shared memory (or when forced for tests)
     L.memb = take(walk_in_gmem(ix) ? round_up(ntp / 32, 2) * ix->ens_words * 32 * 4 : 0);     // whole batch pairs
     L.ev = o;
@@ -1269,6 +1287,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         wp.ev = (uint32_t *)(ws + L.ev);
         wp.cb_w = (uint32_t *)(ws + L.cb_w);
         wp.cb_s = (uint32_t *)(ws + L.cb_s);
+        wp.ap_counter = (unsigned long long *)(ws + L.counter);
         const unsigned ny = (unsigned)ceil_div(S_grid, wp.segs_per_block);
         if (pairs) {
             dim3 grid = gmem ? dim3(ny, (unsigned)nb2) : dim3((unsigned)nb2, ny);
@@ -1300,9 +1319,11 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     ap.own_w_q = ix->own_w_q; ap.own_s_q = ix->own_s_q;
     ap.cb_w = (const uint32_t *)(ws + L.cb_w); ap.cb_s = (const uint32_t *)(ws + L.cb_s);
     ap.partial = (double *)(ws + L.partial);
+    ap.next_item = (unsigned long long *)(ws + L.counter);
     ap.depths = depths;
     const int64_t items = nt * ix->class_groups;
-    const unsigned ap_grid = (unsigned)ceil_div(items, kApThreads / 32);
+    // persistent warps: as many blocks as are resident at once
+    const unsigned ap_grid = (unsigned)std::min<int64_t>(ceil_div(items, kApThreads / 32), (int64_t)std::max(ix->sms, 1) * ORIE_AP_BLOCKS);
     if (depths) ap_kernel<false, 0, true><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());
     else if (full) ap_kernel<true, 0><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());
     else if (ix->ap_mode == 1) ap_kernel<false, 0><<<ap_grid, kApThreads, 0, stream>>>(ap, grid101());   // fixed cls_order groups
