@@ -127,6 +127,7 @@ struct LayoutArgs {
     uint32_t *cls_off, *pad_off, *lcls_off, *lpad_off;          // [C+1]
     int32_t *cls_seg0, *lcls_seg0;                              // [C+1]
     int32_t *seg_chunk0, *seg_nch, *lseg_chunk0, *lseg_nch;     // [S_cap], [SL_cap]
+    int32_t *seg_order;        // [S_cap] detection segments, longest first (the walk hands them out in this order)
     IndexMeta *meta;
 };
 constexpr int kLayoutThreads = 1024;
@@ -169,6 +170,22 @@ __global__ void __launch_bounds__(kLayoutThreads) layout_kernel(const LayoutArgs
         a.meta->P = carry[0][1]; a.meta->nchunks = carry[0][1] / 32u; a.meta->S = carry[0][2];
         a.meta->PL = carry[1][1]; a.meta->nchunksL = carry[1][1] / 32u; a.meta->SL = carry[1][2];
     }
+    // detection segments by descending length (counting sort over the <= 2047 possible lengths): the walk's warps take
+    // segments from the front of this list, so the long ones are under way first and the short ones fill the end
+    __shared__ uint32_t bins[2048];
+    const int64_t S = min((int64_t)carry[0][2], a.S_cap);
+    for (int b = tid; b < 2048; b += kLayoutThreads) bins[b] = 0;
+    __syncthreads();                               // also orders the segment tables written above before the reads below
+    for (int64_t sgm = tid; sgm < S; sgm += kLayoutThreads) atomicAdd(&bins[2047 - min(a.seg_nch[sgm], 2047)], 1u);
+    __syncthreads();
+    {
+        const uint32_t c0 = bins[2 * tid], c1 = bins[2 * tid + 1];
+        const uint32_t x = block_exclusive_scan<kLayoutThreads>(c0 + c1, ws, nullptr);
+        bins[2 * tid] = x; bins[2 * tid + 1] = x + c0;
+    }
+    __syncthreads();
+    for (int64_t sgm = tid; sgm < S; sgm += kLayoutThreads)
+        a.seg_order[atomicAdd(&bins[2047 - min(a.seg_nch[sgm], 2047)], 1u)] = (int32_t)sgm;
 }
 
 // ----------------------------------------------------------------------------
@@ -611,6 +628,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     A.add(&ix->ev_mask, ix->Ev_cap);
     A.add(&ix->seg_chunk0, ix->S_cap);
     A.add(&ix->seg_nch, ix->S_cap);
+    A.add(&ix->seg_order, ix->S_cap);
     A.add(&ix->seg_ev0, ix->S_cap + 1);
     A.add(&ix->cls_seg0, C + 1);
     A.add(&ix->cls_order, C);
@@ -701,7 +719,7 @@ static int build(orie_index *ix, const int64_t *w_off, const int32_t *w_cls, con
     // ---- layout: class counts -> padded layouts and segment tables, on the device
     {
         LayoutArgs la{C, ix->S_cap, ix->SL_cap, seg_chunks, hist, d_cls_off, d_pad_off, d_lcls_off, d_lpad_off,
-                      ix->cls_seg0, ix->lcls_seg0, ix->seg_chunk0, ix->seg_nch, ix->lseg_chunk0, ix->lseg_nch, ix->meta};
+                      ix->cls_seg0, ix->lcls_seg0, ix->seg_chunk0, ix->seg_nch, ix->lseg_chunk0, ix->lseg_nch, ix->seg_order, ix->meta};
         layout_kernel<<<1, kLayoutThreads, 0, st>>>(la);
         ORIE_LAUNCH_CHECK();
     }

@@ -49,6 +49,7 @@ struct orie_index {
     uint16_t *ev_mask = nullptr;     // [Ev_cap] ... and true-positive mask of the slots that hold an event, in slot order
     int32_t *seg_chunk0 = nullptr;   // [S_cap]
     int32_t *seg_nch = nullptr;      // [S_cap]
+    int32_t *seg_order = nullptr;    // [S_cap] segments by descending length
     uint32_t *seg_ev0 = nullptr;     // [S_cap + 1] events in front of the segment; [S] = all events
     int32_t *cls_seg0 = nullptr;     // [C+1]
     int32_t *cls_order = nullptr;    // [C] classes by descending weak-detection count

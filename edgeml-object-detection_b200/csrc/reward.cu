@@ -194,7 +194,8 @@ struct WalkParams {
     uint32_t *ev;               // [ntp][Ev] event records: rank inside the segment (16 bits) | TP mask << 16
     uint16_t *kseg;             // [S][T][ntp] member true positives of the segment per IoU threshold
     uint32_t *cb_w, *cb_s;
-    unsigned long long *ap_counter;   // work counter of the AP kernel that follows: zeroed here
+    const int32_t *seg_order;   // detection segments, longest first
+    uint32_t *pair_next;        // [ceil(ntp / 64)] next entry of seg_order to hand out, per batch pair (zero on entry)
 };
 
 
@@ -248,7 +249,6 @@ walk_kernel(const WalkParams p) {
         return;
     }
     if (yb * p.segs_per_block >= S) return;
-    if (DETS && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.ap_counter = 0ull;
     // the targets' event lists are packed with the index's exact event count as their stride, whatever the capacity of
     // the workspace (sized from an upper bound when the host has not waited for the build): the records of one call stay
     // within a few hundred pages instead of one page per target
@@ -446,11 +446,9 @@ template <bool GMEM, bool PACKED>
 __global__ void __launch_bounds__(kWalk2Threads, kWalk2Blocks)
 walk2_kernel(const WalkParams p) {
     extern __shared__ uint2 memb2_s[];     // [ens_words * 32]: .x / .y = membership words of the pair's two batches
-    __shared__ int next_seg;               // the block's segments are handed to its warps as they become free
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarps = kWalk2Threads / 32;
-    const int64_t lp = GMEM ? blockIdx.y : blockIdx.x;   // local batch pair
-    const int64_t yb = GMEM ? blockIdx.x : blockIdx.y;   // segment group
+    const int64_t lp = GMEM ? blockIdx.y : blockIdx.x;   // local batch pair (GMEM: the pair's blocks are neighbours in launch order)
     const uint32_t status = p.meta->status;
     const int64_t S = p.meta->S;
     if (status & (kStatusRows | kStatusClass | kStatusCounts)) return;
@@ -458,9 +456,6 @@ walk2_kernel(const WalkParams p) {
         if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicOr(&p.meta->status, kStatusWorkspace);
         return;
     }
-    if (yb * p.segs_per_block >= S) return;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.ap_counter = 0ull;
-    if (threadIdx.x == 0) next_seg = 0;
     const int64_t ev_stride = (int64_t)p.meta->Ev;        // packed event lists (see walk_kernel)
     const int64_t tlA = lp * 64 + lane, tlB = tlA + 32;   // local targets of this lane
     const bool hasB = lp * 64 + 32 < p.ntp;              // the pair's second batch exists in this call
@@ -484,15 +479,17 @@ walk2_kernel(const WalkParams p) {
     };
     const uint32_t sentinel = (uint32_t)p.M;
     const int64_t gbA = (p.t0 >> 5) + lp * 2;      // global batch of the first of the two
-    const int64_t sbeg = yb * p.segs_per_block;
-    const int64_t send = min(sbeg + p.segs_per_block, S);
-    // segments of one class have equal length but classes differ: a fixed split over the warps leaves warps idle until the
-    // block's longest share is done, so every warp takes the block's next segment when it becomes free
+    // Several blocks work on one batch pair (all resident at once); their warps take the pair's segments one by one,
+    // longest first (seg_order), from a counter in global memory.  A fixed split left warps idle until the longest
+    // share of their block was done (segments of different classes differ in length) and cut the launch into two
+    // waves of blocks with a half-empty second one.
+    uint32_t *next_seg = p.pair_next + lp;
     for (;;) {
-        int take = 0;
-        if (lane == 0) take = atomicAdd(&next_seg, 1);
-        const int64_t s = sbeg + __shfl_sync(kFull, take, 0);
-        if (s >= send) break;
+        uint32_t take = 0;
+        if (lane == 0) take = atomicAdd(next_seg, 1u);
+        take = __shfl_sync(kFull, take, 0);
+        if ((int64_t)take >= S) break;
+        const int64_t s = p.seg_order[take];
         const int64_t ch0 = p.seg_chunk0[s];
         const int nch = p.seg_nch[s];
         uint32_t cntA = 0, cntB = 0, ecurA = 0, ecurB = 0;
@@ -1004,7 +1001,7 @@ __global__ void rewards_from_sums_kernel(const double *__restrict__ sums, int64_
 // whatever the caller's workspace has left (at least the index's event count, checked on the host once the exact
 // count is known, on the device otherwise).
 struct WsLayout {
-    size_t tot, evcnt, totL, kseg, cb_w, cb_s, partial, counter, memb, ev, fixed;
+    size_t tot, evcnt, totL, kseg, cb_w, cb_s, partial, counter, memb, ev, fixed;     // counter: AP work counter + per-pair segment counters
 };
 
 static bool walk_in_gmem(const orie_index *ix) {
@@ -1025,7 +1022,7 @@ static WsLayout ws_layout(const orie_index *ix, int64_t nt) {
     L.cb_w = take(ix->Dw * 4);
     L.cb_s = take(ix->Ds * 4);
     L.partial = take(ntp * ix->class_groups * 3 * 8);
-    L.counter = take(8);
+    L.counter = take(8 + (ntp / 32 + 1) / 2 * 4);
     // membership tables in global memory, only when they exceed shared memory (or when forced for tests)
     L.memb = take(walk_in_gmem(ix) ? round_up(ntp / 32, 2) * ix->ens_words * 32 * 4 : 0);     // whole batch pairs
     L.ev = o;
@@ -1242,6 +1239,7 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
     const int64_t S_grid = ix->resolved ? ix->S : ix->S_cap, SL_grid = ix->resolved ? ix->SL : ix->SL_cap;
     if (marks) ORIE_CUDA(cudaEventRecord(marks[0], stream));
     const int64_t nb2 = ceil_div(nb, 2);
+    ORIE_CUDA(cudaMemsetAsync(ws + L.counter, 0, 8 + (size_t)nb2 * 4, stream));      // work counters of the walk and the AP kernel
     if (gmem) {
         wp.memb_global = (uint32_t *)(ws + L.memb);
         wp.memb_pairs = pairs ? 1 : 0;
@@ -1287,9 +1285,17 @@ static int run_reward(const orie_index_t *ix, int64_t t0, int64_t nt, const uint
         wp.ev = (uint32_t *)(ws + L.ev);
         wp.cb_w = (uint32_t *)(ws + L.cb_w);
         wp.cb_s = (uint32_t *)(ws + L.cb_s);
-        wp.ap_counter = (unsigned long long *)(ws + L.counter);
-        const unsigned ny = (unsigned)ceil_div(S_grid, wp.segs_per_block);
+        wp.seg_order = ix->seg_order;
+        wp.pair_next = (uint32_t *)(ws + L.counter + 8);
+        unsigned ny = (unsigned)ceil_div(S_grid, wp.segs_per_block);
         if (pairs) {
+            // blocks per pair: what is resident at once shared out over the pairs, at least one segment per warp
+            const int64_t resident = (int64_t)std::max(ix->sms, 1) * kWalk2Blocks;
+            // (tables in global memory: at least 32 blocks per pair, launched pair by pair, so that only the tables of
+            // the few pairs in flight compete for L2 — with every pair resident at once the 50k sweep's walk took
+            // 74 ms instead of 59)
+            ny = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(resident / nb2, gmem ? 32 : 1),
+                                                                  ceil_div(S_grid, kWalk2Threads / 32)));
             dim3 grid = gmem ? dim3(ny, (unsigned)nb2) : dim3((unsigned)nb2, ny);
             if (gmem && wp.slot_pk) walk2_kernel<true, true><<<grid, kWalk2Threads, 0, stream>>>(wp);
             else if (gmem) walk2_kernel<true, false><<<grid, kWalk2Threads, 0, stream>>>(wp);
