@@ -517,7 +517,8 @@ def run_b200(args):
     info = None
     for k in range(args.steps):
         flush.fill_(k)                      # L2 flush, not timed
-        torch.cuda.synchronize()
+        barrier()                           # the ranks start a step together (not timed): without it every rank's interval
+        #                                     also holds its wait, inside the all-reduce, for the rank that started last
         ms, info = timed_step(2000 + k, True)
         dev_ms += ms
     last_seed = 2000 + args.steps - 1

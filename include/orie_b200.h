@@ -127,7 +127,7 @@ typedef struct {
     int32_t walk_unpacked;    /* != 0: the walk reads image and true-positive mask of a slot from two arrays even when
                                * they fit one 32-bit word (<= 65535 images), i.e. the path of larger datasets */
     int32_t walk_single;      /* != 0: the detection walk takes one 32-target batch per warp even where two would fit */
-    double walk_waves;        /* resident-block waves the walk grid is sized for; 0 = default (2) */
+    double walk_waves;        /* resident-block waves the grid of the one-batch walk (labels, fallback) is sized for; 0 = default (2) */
 } orie_tuning_t;
 
 /* Asynchronous: returns as soon as the build is enqueued on `stream`; *out is usable by every call below at once
