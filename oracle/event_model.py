@@ -10,7 +10,8 @@ data flow in numpy / plain Python so the formulation itself can be checked
 against the straightforward oracle on the CPU before any GPU time is spent:
 
   build_index   <-> csrc/index.cu      (slots, segments, events, own lists)
-  walk_target   <-> csrc/reward.cu K1  (segment totals, event ranks, own-detection ranks)
+  walk_target   <-> csrc/reward.cu K1  (segment totals, event ranks, member true positives per segment and
+                                        threshold from the dense event stream, own-detection ranks)
   ap_reverse    <-> csrc/reward.cu K2  (reverse sweep == lib/metrics.py:118-123,137-144)
   reward_target <-> K2 + K3            (reward.py:43-50)
 
@@ -95,6 +96,12 @@ def build_index(M, C, off_w, cls_w, conf_w, tpm_w, off_s, cls_s, conf_s, tpm_s, 
     img_l = np.repeat(np.arange(M), np.diff(lab_off))
     np.add.at(gt, (img_l, lab_cls), 1)
     ix.gtcnt = gt
+    # --- dense event stream (index.cu post_kernel phase C): the slots holding a true positive, in slot order, with
+    #     the number of events in front of every segment (seg_ev0[S] = all events)
+    ev_slot = np.nonzero(ix.slot_tpm != 0)[0]
+    ix.ev_img, ix.ev_mask = ix.slot_img[ev_slot], ix.slot_tpm[ev_slot]
+    seg_first = ix.seg_chunk0 * CHUNK
+    ix.seg_ev0 = np.concatenate([np.searchsorted(ev_slot, seg_first, side="left"), [len(ev_slot)]]).astype(np.int64)
     return ix
 
 
@@ -102,7 +109,9 @@ def walk_target(ix: Index, member: np.ndarray, j: int):
     """K1 for one target: member[M+1] bool (member[M] = False sentinel).
 
     Returns tot[S], events (list per seg of (p_rel, mask)), cb_w, cb_s (rank of
-    each own detection among ensemble members of its segment, exclusive)."""
+    each own detection among ensemble members of its segment, exclusive).  ``ix.kseg`` (set as a side effect, like the
+    kernel's workspace array) holds the member true positives of every segment per threshold bit, counted the way
+    walk_kernel / walk2_kernel count them: from the dense event stream, not from the records."""
     mem = member[ix.slot_img]                      # per slot
     tot = np.zeros(ix.S, dtype=np.int64)
     events = []
@@ -116,6 +125,15 @@ def walk_target(ix: Index, member: np.ndarray, j: int):
         tot[s] = inc[-1]
         hit = np.nonzero((m == 1) & (ix.slot_tpm[a:b] != 0))[0]
         events.append([(int(inc[h]), int(ix.slot_tpm[a + h])) for h in hit])
+    memb_ev = member[ix.ev_img]
+    kseg = np.zeros((ix.S, 16), dtype=np.int64)
+    for s in range(ix.S):
+        e0, e1 = ix.seg_ev0[s], ix.seg_ev0[s + 1]
+        masks = ix.ev_mask[e0:e1][memb_ev[e0:e1]].astype(np.int64)
+        for t in range(16):
+            kseg[s, t] = int(((masks >> t) & 1).sum())
+        assert e1 - e0 >= len(events[s]) and int(memb_ev[e0:e1].sum()) == len(events[s])
+    ix.kseg = kseg
     wq = ix.own_w_q[ix.off_w[j]:ix.off_w[j + 1]]
     sq = ix.own_s_q[ix.off_s[j]:ix.off_s[j + 1]]
     return tot, events, cum[wq], cum[sq]
@@ -209,7 +227,9 @@ def ap_reverse(ix, c, t, tot, events, own, n_l):
     q, mk, cb = own
     s0, s1 = ix.cls_seg0[c], ix.cls_seg0[c + 1]
     n_ens = int(tot[s0:s1].sum())
-    K = sum(1 for s in range(s0, s1) for (_, m) in events[s] if (m >> t) & 1) + sum(1 for m in mk if (m >> t) & 1)
+    K_ens = int(ix.kseg[s0:s1, t].sum())                 # what K1 hands over; K2 no longer reads every record for it
+    assert K_ens == sum(1 for s in range(s0, s1) for (_, m) in events[s] if (m >> t) & 1)
+    K = K_ens + sum(1 for m in mk if (m >> t) & 1)
     n_p = n_ens + len(q)
     v = _Var(K, n_p, n_l)
     if v.dead:
@@ -245,7 +265,8 @@ def delta_reverse(ix, c, t, tot, events, own_w, own_s, n_l):
         return 0.0, 0
     s0, s1 = ix.cls_seg0[c], ix.cls_seg0[c + 1]
     n_ens = int(tot[s0:s1].sum())
-    K_ens = sum(1 for s in range(s0, s1) for (_, m) in events[s] if (m >> t) & 1)
+    K_ens = int(ix.kseg[s0:s1, t].sum())
+    assert K_ens == sum(1 for s in range(s0, s1) for (_, m) in events[s] if (m >> t) & 1)
     var, cur = [], []
     for q, mk, cb in (own_w, own_s):
         var.append(_Var(K_ens + sum(1 for m in mk if (m >> t) & 1), n_ens + len(q), n_l))
