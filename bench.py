@@ -8,10 +8,12 @@ One *step* = the whole hot path over the workload, from the packed dataset
 already resident in HBM to the reward vector: FP64 IoU + TP matching for both
 detectors, dataset index build (sort by class/confidence), device-side
 ensemble draw, membership walk, 101-point AP integration, (N+1)*dmAP, and for
-N>1 GPUs one NCCL collective (all-reduce of per-target AP sums when the classes
-are sharded over the ranks, all-gather of reward slices when the targets are).
-``value`` is rewards (= target images) per second over the K timed steps (CUDA
-events per step, summed; max over ranks).  ``e2e`` is the same job through the
+N>1 GPUs one NCCL collective (all-reduce of zero-padded per-target AP sums: the
+ranks form class groups x target blocks).  Where the job can be recorded it is
+replayed as ONE CUDA graph per step.  ``value`` is rewards (= target images) per
+second over the K timed steps (CUDA events per step, summed; L2 flushed and, at
+N>1, the ranks aligned by a barrier before each step, neither timed; max over
+ranks).  ``e2e`` is the same job through the
 public Python API starting from PINNED HOST buffers (H2D of the packed dataset
 and D2H of the rewards inside the timed region, wall clock).
 
