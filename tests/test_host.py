@@ -131,6 +131,32 @@ def test_c_abi_exports_every_declared_symbol():
     assert rc == 3 and b"T=99" in lib.orie_last_error()
 
 
+def test_ctypes_structs_match_the_header():
+    """orie_tuning_t and orie_index_info_t cross the C ABI by value layout: the ctypes mirrors in _lib.py must list the
+    header's fields in the header's order with the header's types."""
+    import ctypes as C
+    from orie_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "orie_b200.h")).read()
+    ctype = {"int32_t": C.c_int32, "int64_t": C.c_int64, "double": C.c_double}
+
+    def fields(name):
+        body = re.search(r"typedef struct \{([^{}]*)\} " + name + ";", hdr).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            ty, names = decl.split(None, 1)
+            out += [(n.strip(), ctype[ty]) for n in names.split(",")]
+        return out
+
+    assert fields("orie_tuning_t") == list(_lib.Tuning._fields_)
+    info_cls = next(v for v in vars(_lib).values() if isinstance(v, type) and issubclass(v, C.Structure)
+                    and any(f[0] == "num_images" for f in getattr(v, "_fields_", [])))
+    assert fields("orie_index_info_t") == list(info_cls._fields_)
+
+
 def test_engine_fails_loudly_without_a_gpu():
     import torch
     if torch.cuda.is_available():
