@@ -157,6 +157,25 @@ def test_ctypes_structs_match_the_header():
     assert fields("orie_index_info_t") == list(info_cls._fields_)
 
 
+def test_integration_stub_matches_the_header():
+    """INTEGRATION.md shows the ctypes stub a maintainer of the reference would add; every ``argtypes`` list in it must
+    have as many entries as the header's prototype has parameters."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, "include", "orie_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {m.group(1): m.group(2) for m in re.finditer(r"\b(orie_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", hdr, re.S)}
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    env = {"C": C, "_vp": C.c_void_p, "_i64": C.c_int64}
+    seen = 0
+    for m in re.finditer(r"_lib\.(orie_[a-z_0-9]+)\.argtypes = (\[.*?\])(?:;|\s*#|\s*$)", doc, re.M):
+        name, expr = m.group(1), m.group(2)
+        assert name in protos, name
+        params = [a for a in protos[name].split(",") if a.strip() and a.strip() != "void"]
+        assert len(eval(expr, env)) == len(params), (name, expr, protos[name])
+        seen += 1
+    assert seen >= 8
+
+
 def test_engine_fails_loudly_without_a_gpu():
     import torch
     if torch.cuda.is_available():
